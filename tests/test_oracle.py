@@ -1,0 +1,172 @@
+"""CPU tests that pin the oracle (no GPU): two formulations agree, invariants
+hold, the data path matches known facts of the MNIST files."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import fixedl_oracle as O
+from tests.helpers import copy_mps, make_problem, rel
+
+
+def test_mnist_known_answers(ref_mnist_dir):
+    md5 = {"train-images-idx3-ubyte": "6bbc9ace898e44ae57da46a324031adb",
+           "train-labels-idx1-ubyte": "a25bea736e30d166cdddb491f175f624"}
+    for f, want in md5.items():
+        got = hashlib.md5(open(os.path.join(ref_mnist_dir, f), "rb").read()).hexdigest()
+        assert got == want
+    labs = O.read_idx(os.path.join(ref_mnist_dir, "train-labels-idx1-ubyte"))
+    assert np.bincount(labs, minlength=10).tolist() == [5923, 6742, 5958, 6131, 5842, 5421, 5918, 6265, 5851, 5949]
+    data, labels, idx = O.read_mnist(ref_mnist_dir, "Train", 100)
+    assert data.shape == (1000, 784) and idx[:10].tolist() == list(range(10)) and idx[-1] == 1105
+    assert np.bincount(labels, minlength=10).tolist() == [100] * 10
+    assert data.max() <= 1.0
+
+
+def test_golden_mnist_subset_matches_reference(ref_mnist_dir):
+    """tests/golden/mnist_100_per_label_14x14.npz was produced by
+    tests/golden/make_golden.py from the reference's MNIST files."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mnist_100_per_label_14x14.npz"))
+    data, labels, _ = O.read_mnist(ref_mnist_dir, "Train", 100)
+    d14 = O.reduce_image(data, 14)
+    assert np.array_equal(g["labels"], labels)
+    assert np.allclose(g["sum4"].astype(np.float64) / (4 * 255.0), d14, rtol=0, atol=1e-15)
+
+
+def test_reduce_and_phi():
+    img = np.arange(16, dtype=np.float64).reshape(1, 16) / 255.0
+    r = O.reduce_image(img, 2)
+    # 4x4 -> 2x2 block means, raster order
+    assert np.allclose(r * 255.0, [[2.5, 4.5, 10.5, 12.5]])
+    f = O.phi(np.array([0.0, 1.0]))
+    assert np.allclose(f, [[1.0, 0.0], [1.0, 1.0 / 255.0 / 4.0]])
+    with pytest.raises(ValueError):
+        O.phi(np.array([-1.0]))
+
+
+def test_shard_bounds():
+    assert O.shard_bounds(3, 10) == [(0, 3), (3, 6), (6, 10)]
+    assert O.shard_bounds(1, 7) == [(0, 7)]
+
+
+def test_sweep_schedule():
+    s = O.sweep_schedule(5)
+    assert s == [(1, 1), (2, 1), (3, 1), (4, 1), (4, 2), (3, 2), (2, 2), (1, 2)]
+
+
+def test_truncation_rule():
+    P = np.array([1.0, 0.5, 1e-3, 1e-12, 1e-13, 1e-14])
+    assert O.truncate_spectrum(P, 10, 1, 1e-10)[0] == 3
+    assert O.truncate_spectrum(P, 2, 1, 1e-10)[0] == 2            # maxm wins
+    assert O.truncate_spectrum(P, 10, 5, 1e-10)[0] == 5           # minm wins
+    m, te = O.truncate_spectrum(P, 2, 1, 1e-10)
+    assert np.isclose(te, 1e-3 + 1e-12 + 1e-13 + 1e-14)
+    m, te = O.truncate_spectrum(P, 10, 1, 1e-10, do_rel_cutoff=True)
+    assert m == 3 and np.isclose(te, (1e-12 + 1e-13 + 1e-14) / P.sum())
+
+
+def _walk(ts, W, upto):
+    """advance the right sweep without optimising, so that bond `upto` is current"""
+    for b in range(1, upto):
+        ts.set_bond(b)
+        ts.shiftE(W, b, "Fromleft")
+    ts.set_bond(upto)
+
+
+@pytest.mark.parametrize("b", [1, 2, 3, 4, 5, 6, 7])
+def test_literal_equals_structured(b):
+    feat, labels, W = make_problem(N=8, NT=60, m0=3)
+    ts = O.TrainStates(feat, labels)
+    ts.init(W)
+    _walk(ts, W, b)
+    B = O.form_bond(W[b], W[b + 1])
+    P1 = O.project(B, ts, literal=True)
+    P2 = O.project(B, ts, literal=False)
+    assert rel(P1, P2) < 1e-12
+    dP = np.random.default_rng(b).standard_normal(P1.shape)
+    G1 = O.backproject(dP, B.shape, ts, literal=True)
+    G2 = O.backproject(dP, B.shape, ts, literal=False)
+    assert rel(G1, G2) < 1e-12
+    # the env recursion equals the full contraction (util.h:19-40)
+    for n in (0, 7, 33):
+        assert rel(P2[n], O.toverlap(W, feat[n], ts.jc)) < 1e-11
+
+
+@pytest.mark.parametrize("b", [2, 3, 4, 6])
+def test_gradient_is_minus_half_dC(b):
+    """finite-difference check: dC/dB = -2 * sum_n dP_n v_n"""
+    feat, labels, W = make_problem(N=8, NT=40, m0=3)
+    ts = O.TrainStates(feat, labels)
+    ts.init(W)
+    _walk(ts, W, b)
+    B = O.form_bond(W[b], W[b + 1])
+    G, _ = O._grad(B, ts, 0.0, False)
+    rng = np.random.default_rng(1)
+    for _ in range(3):
+        dB = rng.standard_normal(B.shape)
+        eps = 1e-6 * np.linalg.norm(B) / np.linalg.norm(dB)
+        c1 = O.quadcost(B + eps * dB, ts)
+        c0 = O.quadcost(B - eps * dB, ts)
+        fd = (c1 - c0) / (2 * eps)
+        an = -2.0 * float(np.sum(G * dB))
+        assert abs(fd - an) < 1e-6 * max(abs(an), 1e-12) + 1e-9
+
+
+def test_cg_decreases_quadratic_cost():
+    feat, labels, W = make_problem(N=8, NT=200, m0=3)
+    ts = O.TrainStates(feat, labels)
+    ts.init(W)
+    _walk(ts, W, 3)
+    B0 = O.form_bond(W[3], W[4])
+    c0 = O.quadcost(B0, ts)
+    B, costs, rn = O.cgrad(B0, ts, 4)
+    c4 = O.quadcost(B, ts)
+    assert c4 < c0 and all(costs[i + 1] <= costs[i] + 1e-12 for i in range(len(costs) - 1))
+
+
+@pytest.mark.parametrize("b,ha", [(2, 1), (3, 1), (4, 1), (4, 2), (3, 2), (6, 2)])
+def test_svd_split_reconstructs(b, ha):
+    feat, labels, W = make_problem(N=8, NT=50, m0=3)
+    jc = 4
+    rng = np.random.default_rng(b * 7 + ha)
+    B = O.form_bond(W[b], W[b + 1])
+    B = B + 0.1 * rng.standard_normal(B.shape)
+    Wb, Wb1, m, te = O.svd_split(B, b, ha, jc, 100, 1, 0.0)
+    assert rel(O.form_bond(Wb, Wb1), B) < 1e-12
+    # the "c" side is an isometry
+    if ha == 1:
+        U = (np.transpose(Wb, (0, 1, 3, 2)) if Wb.ndim == 4 else Wb).reshape(-1, m) if Wb.ndim == 3 else \
+            np.transpose(Wb, (0, 1, 3, 2)).reshape(-1, m)
+        assert rel(U.T @ U, np.eye(m)) < 1e-12
+    else:
+        V = Wb1.reshape(m, -1)
+        assert rel(V @ V.T, np.eye(m)) < 1e-12
+    # truncation error equals the squared distance
+    Wb, Wb1, m2, te = O.svd_split(B, b, ha, jc, 3, 1, 0.0)
+    assert m2 == 3
+    assert np.isclose(np.sum((O.form_bond(Wb, Wb1) - B) ** 2), te, rtol=1e-9)
+
+
+def test_bond_position_invariance():
+    """quadcost(newB) at bond b == quadcost(W(b+1)W(b+2)) at the next bond."""
+    feat, labels, W = make_problem(N=10, NT=150, m0=3)
+    ts = O.TrainStates(feat, labels)
+    ts.init(W)
+    rec = O.mldmrg(W, ts, 1, 8, 1, 1e-14, max_bonds=4)
+    ts.set_bond(5)
+    c = O.quadcost(O.form_bond(W[5], W[6]), ts) / ts.NT
+    assert abs(c - rec[-1]["cost"]) < 1e-10 * max(1.0, abs(c))
+
+
+def test_sharded_sweep_equals_single(tmp_path):
+    feat, labels, W = make_problem(N=8, NT=120, m0=3)
+    W2 = copy_mps(W)
+    a = O.TrainStates(feat, labels, 1)
+    a.init(W)
+    b = O.TrainStates(feat, labels, 3)
+    b.init(W2)
+    ra = O.mldmrg(W, a, 1, 6, 1, 1e-12, max_bonds=3)
+    rb = O.mldmrg(W2, b, 1, 6, 1, 1e-12, max_bonds=3)
+    for x, y in zip(ra, rb):
+        assert abs(x["cost"] - y["cost"]) < 1e-7 and x["m"] == y["m"]

@@ -1,0 +1,213 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI, against the
+float64 oracle on the same seeded inputs.  Tolerances (all float64):
+  forward quantities (P, cost, envs, gradient)      rel 1e-11
+  B after the 4-pass CG                             rel 1e-6   (the CG itself
+      amplifies 1e-16 reordering noise to ~1e-7 between two float64 oracles,
+      see DESIGN.md "Precision")
+  cost after a whole bond update                    rel 1e-8
+"""
+import numpy as np
+import pytest
+
+from oracle import fixedl_oracle as O
+from tests.helpers import copy_mps, make_problem, rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from tnml_b200 import capi as c
+    c.load_library()
+    return c
+
+
+def _gpu_state(capi, feat, labels, W):
+    h = capi.Handle(0)
+    h.set_images(feat, labels.astype(np.int32))
+    h.set_mps(W)
+    h.init_envs()
+    return h
+
+
+def _walk_both(h, ts, W, capi, upto):
+    for b in range(1, upto):
+        ts.set_bond(b)
+        ts.shiftE(W, b, "Fromleft")
+        h.set_bond(b)
+        h.shift_env(b, capi.FROMLEFT)
+    ts.set_bond(upto)
+    h.set_bond(upto)
+
+
+def test_version_and_errors(capi):
+    assert b"sm_100a" in capi.load_library().tnml_version()
+    h = capi.Handle(0)
+    with pytest.raises(capi.TnmlError):
+        h.init_envs()                      # no images
+    feat, labels, W = make_problem(N=8, NT=20, m0=2)
+    h.set_images(feat, labels.astype(np.int32))
+    with pytest.raises(capi.TnmlError):
+        h.set_site(3, W[4])                # label index on the wrong site (fixedL.cc:734)
+    with pytest.raises(capi.TnmlError):
+        h.init_envs()                      # sites missing
+    h.close()
+
+
+def test_init_envs_match_oracle(capi):
+    feat, labels, W = make_problem(N=10, NT=257, m0=4)
+    ts = O.TrainStates(feat, labels)
+    ts.init(W)
+    h = _gpu_state(capi, feat, labels, W)
+    for j in range(3, 11):
+        assert rel(h.get_env(j), ts.slot[j]) < 1e-12, j
+    h.close()
+
+
+@pytest.mark.parametrize("b", [1, 2, 3, 4, 5, 6, 7, 8, 9])
+def test_forward_and_gradient_all_bond_classes(capi, b):
+    """classes L (b<=3), C (b=4,5), R (b>=6) incl. the edge bonds (ml=1 / mr=1)."""
+    feat, labels, W = make_problem(N=10, NT=333, m0=4)
+    ts = O.TrainStates(feat, labels)
+    ts.init(W)
+    h = _gpu_state(capi, feat, labels, W)
+    _walk_both(h, ts, W, capi, b)
+    if b > 1:
+        assert rel(h.get_env(b - 1), ts.slot[b - 1]) < 1e-12
+    B = O.form_bond(W[b], W[b + 1])
+    h.bond_form()
+    assert rel(h.bond_store(), B) < 1e-13
+    C, CL, ncor = O.quadcost(B, ts, detail=True)
+    c, cl, nc = h.quadcost(False)
+    assert abs(c - C) < 1e-11 * C and rel(cl, CL) < 1e-11 and nc == ncor
+    lab, P = h.predict(want_P=True)
+    Pref = O.project(B, ts)
+    assert rel(P, Pref) < 1e-11
+    assert np.array_equal(lab, O.argmax_first(np.abs(Pref)))
+    # one CG pass == gradient + step: checks backward too
+    Bo, costs_o, rn_o = O.cgrad(B, ts, 2)
+    h.bond_load(B)
+    costs, rn = h.cgrad(2)
+    assert rel(h.bond_store(), Bo) < 1e-9
+    assert rel(costs, costs_o) < 1e-10 and rel(rn, rn_o) < 1e-7
+    h.close()
+
+
+@pytest.mark.parametrize("lam", [0.0, 1e-3])
+def test_cgrad_matches_oracle(capi, lam):
+    feat, labels, W = make_problem(N=10, NT=500, m0=4)
+    ts = O.TrainStates(feat, labels)
+    ts.init(W)
+    h = _gpu_state(capi, feat, labels, W)
+    _walk_both(h, ts, W, capi, 3)
+    B = O.form_bond(W[3], W[4])
+    Bo, costs_o, rn_o = O.cgrad(B, ts, 4, lam)
+    h.bond_load(B)
+    costs, rn = h.cgrad(4, lam)
+    assert len(costs) == len(costs_o)
+    assert rel(costs, costs_o) < 1e-9
+    assert rel(h.bond_store(), Bo) < 1e-6
+    assert abs(h.quadcost(False, lam)[0] - O.quadcost(Bo, ts, lam)) < 1e-9 * O.quadcost(Bo, ts, lam)
+    h.close()
+
+
+@pytest.mark.parametrize("b,ha", [(2, 1), (4, 1), (5, 1), (5, 2), (4, 2), (8, 2), (9, 1), (1, 2)])
+def test_svd_split_matches_oracle(capi, b, ha):
+    """gauge-free comparison: newB = W(c)W(c+dc), m, truncerr; isometry of W(c)."""
+    feat, labels, W = make_problem(N=10, NT=64, m0=4)
+    ts = O.TrainStates(feat, labels)
+    ts.init(W)
+    h = _gpu_state(capi, feat, labels, W)
+    _walk_both(h, ts, W, capi, b)
+    rng = np.random.default_rng(100 * b + ha)
+    B = O.form_bond(W[b], W[b + 1])
+    B = B + 0.05 * np.linalg.norm(B) / np.sqrt(B.size) * rng.standard_normal(B.shape)
+    for (maxm, minm, cutoff) in [(100, 1, 0.0), (5, 1, 0.0), (6, 3, 1e-3)]:
+        Wb, Wb1, m, te = O.svd_split(B, b, ha, 5, maxm, minm, cutoff)
+        h.bond_load(B)
+        gm, gte = h.svd_split(capi.FROMLEFT if ha == 1 else capi.FROMRIGHT, cutoff, maxm, minm)
+        assert gm == m
+        assert abs(gte - te) <= 1e-9 * max(te, 1e-300) + 1e-24
+        gWb, gWb1 = h.get_site(b), h.get_site(b + 1)
+        assert gWb.shape == Wb.shape and gWb1.shape == Wb1.shape
+        assert rel(O.form_bond(gWb, gWb1), O.form_bond(Wb, Wb1)) < 1e-11
+        iso = gWb if ha == 1 else gWb1
+        if ha == 1:
+            U = (np.transpose(iso, (0, 1, 3, 2)) if iso.ndim == 4 else iso).reshape(-1, m)
+            assert rel(U.T @ U, np.eye(m)) < 1e-12
+        else:
+            V = iso.reshape(m, -1)
+            assert rel(V @ V.T, np.eye(m)) < 1e-12
+    h.close()
+
+
+def test_bond_update_sequence_matches_oracle(capi):
+    """Whole loop body of mldmrg, bond after bond, on a chain that covers all
+    three bond classes and both sweep directions."""
+    feat, labels, W = make_problem(N=10, NT=1000, m0=3)
+    ts = O.TrainStates(feat, labels)
+    ts.init(copy_mps(W))
+    Wo = copy_mps(W)
+    ref = O.mldmrg(Wo, ts, 1, 8, 4, 1e-10)
+    h = _gpu_state(capi, feat, labels, W)
+    p = capi.BondParams(4, 0.0, 1e-10, 1e-10, 8, 4, 0)
+    worst = 0.0
+    for k, (b, ha) in enumerate(O.sweep_schedule(10)):
+        r = h.bond_update(b, ha, p)
+        o = ref[k]
+        assert r.newm == o["m"], (k, b, ha)
+        e = abs(r.cost / 1000 - o["cost"]) / o["cost"]
+        worst = max(worst, e)
+        assert e < 1e-6, (k, b, ha, e)
+        assert abs(int(r.ncorrect) - o["ncor"]) <= 2
+    print("worst rel cost deviation over the sweep:", worst)
+    # final MPS: compare the model function, not the gauge
+    Wg = h.get_mps()
+    for n in (0, 10, 500):
+        assert rel(O.toverlap(Wg, feat[n], 5), O.toverlap(Wo, feat[n], 5)) < 1e-4
+    h.close()
+
+
+def test_golden_mnist_first_bonds(capi):
+    """Real MNIST (committed 1000-image 14x14 subset): first 12 bond updates of
+    BASELINE config 1 (maxm=20) against the oracle."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mnist_100_per_label_14x14.npz"))
+    feat = O.features(g["sum4"].astype(np.float64) / (4 * 255.0))
+    labels = g["labels"]
+    from tnml_b200 import data as D
+    W = D.random_mps(196, 2, 10, seed=1)
+    ts = O.TrainStates(feat, labels)
+    ts.init(copy_mps(W))
+    ref = O.mldmrg(copy_mps(W), ts, 1, 20, 10, 1e-10, max_bonds=12)
+    h = _gpu_state(capi, feat, labels, W)
+    p = capi.BondParams(4, 0.0, 1e-10, 1e-10, 20, 10, 0)
+    for k in range(12):
+        r = h.bond_update(k + 1, 1, p)
+        assert r.newm == ref[k]["m"]
+        assert abs(r.cost / 1000 - ref[k]["cost"]) < 1e-5 * ref[k]["cost"], k
+    h.close()
+
+
+def test_shards_sum_to_whole(capi):
+    """Size-independent property used for multi-GPU: per-shard costs and
+    gradients are plain sums over images (fixedL.cc:385,402,421)."""
+    feat, labels, W = make_problem(N=10, NT=600, m0=4)
+    hs = []
+    for (a, b) in O.shard_bounds(3, 600):
+        hs.append(_gpu_state(capi, feat[a:b], labels[a:b], W))
+    whole = _gpu_state(capi, feat, labels, W)
+    tot = 0.0
+    ncs = 0
+    for h in hs:
+        h.set_bond(1)
+        h.bond_form()
+        c, _, nc = h.quadcost(False)
+        tot += c
+        ncs += nc
+    whole.set_bond(1)
+    whole.bond_form()
+    c, _, nc = whole.quadcost(False)
+    assert abs(c - tot) < 1e-11 * c and nc == ncs
+    for h in hs + [whole]:
+        h.close()

@@ -1,0 +1,966 @@
+// tnml_capi.cu -- the C-ABI of include/tnml_b200.h: per-GPU state ("TrainStates"
+// on the device), the CG driver of fixedL.cc:349-445, quadcost, svd, shiftE.
+// No CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tnml_b200.h"
+#include "tnml_kernels.cuh"
+
+using namespace tnml;
+
+namespace {
+
+std::string g_err;  // create-time errors
+
+struct Slot {
+  double* p = nullptr;
+  size_t bytes = 0;
+  int m = 0;
+  int fat = 0;
+  int kind = 0;  // 0 empty, 1 left env, 2 right env
+};
+struct Site {
+  double* d = nullptr;
+  size_t cap = 0;  // elements
+  int ml = 0, mr = 0, lab = 0;
+  long size() const { return (long)ml * 2 * mr * (lab ? NL : 1); }
+};
+
+struct DBuf {
+  double* p = nullptr;
+  size_t cap = 0;  // elements
+};
+
+// minimal NCCL surface, resolved with dlopen so the library loads without NCCL
+struct NcclId {
+  char internal[128];
+};
+typedef int (*nccl_get_uid_t)(NcclId*);
+typedef int (*nccl_init_rank_t)(void**, int, NcclId, int);
+typedef int (*nccl_allreduce_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_destroy_t)(void*);
+typedef const char* (*nccl_errstr_t)(int);
+struct NcclApi {
+  void* lib = nullptr;
+  nccl_get_uid_t get_uid = nullptr;
+  nccl_init_rank_t init_rank = nullptr;
+  nccl_allreduce_t allreduce = nullptr;
+  nccl_destroy_t destroy = nullptr;
+  nccl_errstr_t errstr = nullptr;
+};
+NcclApi g_nccl;
+bool load_nccl(std::string& err) {
+  if (g_nccl.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
+  void* lib = nullptr;
+  for (const char* n : names) {
+    lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  if (!lib) {
+    err = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+    return false;
+  }
+  g_nccl.get_uid = (nccl_get_uid_t)dlsym(lib, "ncclGetUniqueId");
+  g_nccl.init_rank = (nccl_init_rank_t)dlsym(lib, "ncclCommInitRank");
+  g_nccl.allreduce = (nccl_allreduce_t)dlsym(lib, "ncclAllReduce");
+  g_nccl.destroy = (nccl_destroy_t)dlsym(lib, "ncclCommDestroy");
+  g_nccl.errstr = (nccl_errstr_t)dlsym(lib, "ncclGetErrorString");
+  if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.allreduce || !g_nccl.destroy) {
+    err = "libnccl lacks a required symbol";
+    dlclose(lib);
+    return false;
+  }
+  g_nccl.lib = lib;
+  return true;
+}
+
+enum Phase { PH_PROJ = 0, PH_GRAD, PH_FAT, PH_SVD, PH_SHIFT, PH_OTHER, PH_COUNT };
+
+}  // namespace
+
+struct tnml_handle_s {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  int num_sm = 148;
+  std::string err;
+
+  long NT = 0, NTg = 0, first = 0;
+  int N = 0, jc = 0;
+  double* feat = nullptr;  // [N+2][NT][2]
+  int32_t* labels = nullptr;
+  double* ones = nullptr;  // [NT]
+  std::vector<Slot> slot;
+  std::vector<Site> W;
+  int currb = -1;
+
+  // current bond
+  BondGeom g{};
+  int cls = 0;  // 0 L, 1 C, 2 R
+  bool bond_valid = false;
+  DBuf B, r, p, G, T, Gpart, Q, Z, Bm;
+  double* P = nullptr;  // [NT][NL]
+  int32_t* pred = nullptr;
+  double* stats_partial = nullptr;
+  int nfat_blocks = 0;
+  double* dscal = nullptr;  // [32] device scalars
+  double* dot_scratch = nullptr;
+  double* hpin = nullptr;  // pinned host [64]
+  SvdWork svd;
+
+  void* comm = nullptr;
+  int nranks = 1, rank = 0;
+
+  tnml_stats stats{};
+  bool timing = false;
+  struct Ev {
+    int ph;
+    cudaEvent_t a, b;
+  };
+  std::vector<Ev> evs;
+  std::vector<cudaEvent_t> evpool;
+};
+
+namespace {
+
+int fail(tnml_handle h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h)
+    h->err = buf;
+  else
+    g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(h, TNML_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define CKL()                                                                                      \
+  do {                                                                                             \
+    cudaError_t e_ = cudaGetLastError();                                                           \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(h, TNML_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define TRY(expr)            \
+  do {                       \
+    int rc_ = (expr);        \
+    if (rc_ != 0) return rc_; \
+  } while (0)
+
+int ensure(tnml_handle h, DBuf& b, size_t n) {
+  if (n <= b.cap) return 0;
+  if (b.p) CK(cudaFreeAsync(b.p, h->st));
+  b.p = nullptr;
+  b.cap = 0;
+  CK(cudaMallocAsync(&b.p, n * sizeof(double), h->st));
+  b.cap = n;
+  return 0;
+}
+
+struct PhaseTimer {
+  tnml_handle h;
+  cudaEvent_t a = nullptr, b = nullptr;
+  int ph;
+  PhaseTimer(tnml_handle h_, int ph_) : h(h_), ph(ph_) {
+    if (!h->timing) return;
+    a = get();
+    b = get();
+    cudaEventRecord(a, h->st);
+  }
+  ~PhaseTimer() {
+    if (!h->timing) return;
+    cudaEventRecord(b, h->st);
+    h->evs.push_back({ph, a, b});
+  }
+  cudaEvent_t get() {
+    if (!h->evpool.empty()) {
+      cudaEvent_t e = h->evpool.back();
+      h->evpool.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+
+void drain_events(tnml_handle h) {
+  if (h->evs.empty()) return;
+  cudaStreamSynchronize(h->st);
+  for (auto& e : h->evs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e.a, e.b);
+    double* dst = &h->stats.ms_proj;
+    dst[e.ph] += ms;
+    h->evpool.push_back(e.a);
+    h->evpool.push_back(e.b);
+  }
+  h->evs.clear();
+}
+
+const double* featp(tnml_handle h, int j) { return h->feat + (long)j * h->NT * 2; }
+
+// env accessors for bond b: returns pointer, dim, fat flag
+struct EnvRef {
+  const double* p;
+  int m;
+  int fat;
+};
+int left_env(tnml_handle h, int b, EnvRef& e) {
+  if (b - 1 < 1) {
+    e = {h->ones, 1, 0};
+    return 0;
+  }
+  Slot& s = h->slot[b - 1];
+  if (s.kind != 1) return fail(h, TNML_ERR_INVALID, "left environment slot %d not built (kind=%d)", b - 1, s.kind);
+  e = {s.p, s.m, s.fat};
+  return 0;
+}
+int right_env(tnml_handle h, int b, EnvRef& e) {
+  if (b + 2 > h->N) {
+    e = {h->ones, 1, 0};
+    return 0;
+  }
+  Slot& s = h->slot[b + 2];
+  if (s.kind != 2) return fail(h, TNML_ERR_INVALID, "right environment slot %d not built (kind=%d)", b + 2, s.kind);
+  e = {s.p, s.m, s.fat};
+  return 0;
+}
+
+int bond_class(tnml_handle h, int b) {
+  if (b + 1 < h->jc) return 0;
+  if (b > h->jc) return 2;
+  return 1;
+}
+
+int setup_geom(tnml_handle h, int b) {
+  Site& wb = h->W[b];
+  Site& wb1 = h->W[b + 1];
+  if (!wb.d || !wb1.d) return fail(h, TNML_ERR_INVALID, "site tensors %d/%d not set", b, b + 1);
+  if (wb.mr != wb1.ml) return fail(h, TNML_ERR_INVALID, "link mismatch between sites %d and %d", b, b + 1);
+  BondGeom g{};
+  g.ml = wb.ml;
+  g.mr = wb1.mr;
+  g.lab_b = wb.lab;
+  g.lab_b1 = wb1.lab;
+  g.nl = (wb.lab || wb1.lab) ? NL : 1;
+  h->cls = bond_class(h, b);
+  if ((h->cls == 1) != (g.nl == NL)) return fail(h, TNML_ERR_INVALID, "Label Index not on site %d", h->jc);
+  const long ml = g.ml, mr = g.mr;
+  if (h->cls == 0) {  // Bc[alpha][s][t][beta]
+    g.sa = 4 * mr, g.ss = 2 * mr, g.st = mr, g.sb = 1, g.sl = 0;
+  } else if (h->cls == 2) {  // Bc[beta][t][s][alpha]
+    g.sb = 4 * ml, g.st = 2 * ml, g.ss = ml, g.sa = 1, g.sl = 0;
+  } else {  // Bc[alpha][s][t][l][beta]
+    g.sa = 4 * NL * mr, g.ss = 2 * NL * mr, g.st = NL * mr, g.sl = mr, g.sb = 1;
+  }
+  h->g = g;
+  EnvRef le, re;
+  TRY(left_env(h, b, le));
+  TRY(right_env(h, b, re));
+  if (le.m != g.ml || re.m != g.mr)
+    return fail(h, TNML_ERR_INVALID, "environment dims (%d,%d) do not match bond dims (%d,%d) at bond %d", le.m,
+                re.m, g.ml, g.mr, b);
+  const bool wantLfat = (h->cls == 2), wantRfat = (h->cls == 0);
+  if ((le.fat != 0) != wantLfat || (re.fat != 0) != wantRfat)
+    return fail(h, TNML_ERR_INVALID, "environment label placement inconsistent at bond %d", b);
+  return 0;
+}
+
+// forward pass: P[n][l] for bond-shaped tensor X (canonical layout).
+// mode: FAT_GRAD (also produces Z), FAT_PAP, FAT_COST.  Leaves stats in dstats.
+int forward(tnml_handle h, const double* X, int mode, double* dstats) {
+  const int b = h->currb;
+  const BondGeom& g = h->g;
+  EnvRef le, re;
+  TRY(left_env(h, b, le));
+  TRY(right_env(h, b, re));
+  const long NT = h->NT;
+  if (h->cls != 1) {
+    const bool L = (h->cls == 0);
+    const EnvRef& thin = L ? le : re;
+    const EnvRef& fat = L ? re : le;
+    const double* fth = featp(h, L ? b : b + 1);
+    const double* ffa = featp(h, L ? b + 1 : b);
+    const int mt = thin.m, mf = fat.m;
+    TRY(ensure(h, h->Q, (size_t)NT * mf));
+    if (mode == FAT_GRAD) TRY(ensure(h, h->Z, (size_t)NT * mf));
+    {
+      PhaseTimer t(h, PH_PROJ);
+      krgemm(h->st, 2, thin.p, mt, mt, fth, 1, X, X + mf, 2L * mf, mf, ffa, h->Q.p, mf, NT);
+      CKL();
+    }
+    {
+      PhaseTimer t(h, PH_FAT);
+      fat_kernel(h->st, mode, h->Q.p, fat.p, mf, h->labels, h->P, h->Z.p, h->pred, h->stats_partial,
+                 h->nfat_blocks, NT);
+      CKL();
+      reduce_stats(h->st, h->stats_partial, h->nfat_blocks, dstats);
+      CKL();
+    }
+    h->stats.launches += 3;
+    h->stats.alg_flops += (double)NT * (8.0 * mt * mf + 2.0 * NL * mf * (mode == FAT_GRAD ? 2 : 1));
+    h->stats.alg_bytes += 8.0 * NT * ((double)mt + (double)NL * mf + 4);
+  } else {
+    const long J = (long)NL * g.mr;
+    TRY(ensure(h, h->Q, (size_t)NT * J));
+    if (mode == FAT_GRAD) TRY(ensure(h, h->Z, (size_t)NT * J));
+    {
+      PhaseTimer t(h, PH_PROJ);
+      krgemm(h->st, 2, le.p, g.ml, g.ml, featp(h, b), 1, X, X + J, 2 * J, (int)J, featp(h, b + 1), h->Q.p, J, NT);
+      CKL();
+    }
+    {
+      PhaseTimer t(h, PH_FAT);
+      fat_kernel(h->st, mode == FAT_GRAD ? FAT_GRAD_OUTER : mode, re.p, h->Q.p, g.mr, h->labels, h->P, h->Z.p,
+                 h->pred, h->stats_partial, h->nfat_blocks, NT);
+      CKL();
+      reduce_stats(h->st, h->stats_partial, h->nfat_blocks, dstats);
+      CKL();
+    }
+    h->stats.launches += 3;
+    h->stats.alg_flops += (double)NT * (8.0 * NL * g.ml * g.mr + 2.0 * NL * g.mr);
+    h->stats.alg_bytes += 8.0 * NT * ((double)g.ml + g.mr + 4);
+  }
+  return 0;
+}
+
+// backward: G = sum_n dP_n (x) v_n from Z (left by forward(FAT_GRAD)); G gets a 16-double tail
+int backward(tnml_handle h) {
+  const int b = h->currb;
+  const BondGeom& g = h->g;
+  EnvRef le, re;
+  TRY(left_env(h, b, le));
+  TRY(right_env(h, b, re));
+  const long NT = h->NT;
+  const long n = g.size();
+  TRY(ensure(h, h->G, (size_t)n + 16));
+  const double* thin;
+  int mt;
+  const double *f1, *f2;
+  long J;
+  if (h->cls == 0) {
+    thin = le.p, mt = le.m, f1 = featp(h, b), f2 = featp(h, b + 1), J = re.m;
+  } else if (h->cls == 2) {
+    thin = re.p, mt = re.m, f1 = featp(h, b + 1), f2 = featp(h, b), J = le.m;
+  } else {
+    thin = le.p, mt = le.m, f1 = featp(h, b), f2 = featp(h, b + 1), J = (long)NL * g.mr;
+  }
+  const int ns = krgram_splits(mt, (int)J, 2, NT, h->num_sm);
+  TRY(ensure(h, h->Gpart, (size_t)ns * n));
+  PhaseTimer t(h, PH_GRAD);
+  krgram(h->st, 2, thin, mt, mt, f1, f2, h->Z.p, J, (int)J, h->Gpart.p, NT, ns);
+  CKL();
+  reduce_partials(h->st, h->Gpart.p, ns, n, h->G.p);
+  CKL();
+  h->stats.launches += 2;
+  h->stats.alg_flops += (double)NT * 8.0 * mt * J;
+  h->stats.alg_bytes += 8.0 * NT * ((double)mt + J + 4);
+  return 0;
+}
+
+int allreduce(tnml_handle h, double* buf, size_t count) {
+  if (!h->comm) return 0;
+  int rc = g_nccl.allreduce(buf, buf, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, h->comm, h->st);
+  if (rc != 0)
+    return fail(h, TNML_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
+  h->stats.launches += 1;
+  return 0;
+}
+
+int fetch(tnml_handle h, const double* dsrc, int n, double* hdst) {
+  CK(cudaMemcpyAsync(h->hpin, dsrc, n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  memcpy(hdst, h->hpin, n * sizeof(double));
+  return 0;
+}
+
+// gradient evaluation at X: G (+16 stats tail, all-reduced), host stats out
+int grad_eval(tnml_handle h, const double* X, double* hstats) {
+  const long n = h->g.size();
+  TRY(ensure(h, h->G, (size_t)n + 16));
+  TRY(forward(h, X, FAT_GRAD, h->dscal));
+  TRY(backward(h));
+  CK(cudaMemcpyAsync(h->G.p + n, h->dscal, 16 * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  TRY(allreduce(h, h->G.p, (size_t)n + 16));
+  TRY(fetch(h, h->G.p + n, 16, hstats));
+  return 0;
+}
+
+int ddot(tnml_handle h, long n, const double* x, const double* y, double* out) {
+  dot(h->st, n, x, y, h->dot_scratch, h->dscal + 16);
+  CKL();
+  h->stats.launches += 2;
+  return fetch(h, h->dscal + 16, 1, out);
+}
+
+int alloc_slot(tnml_handle h, Slot& s, size_t bytes) {
+  if (s.p && s.bytes >= bytes) return 0;
+  if (s.p) CK(cudaFreeAsync(s.p, h->st));
+  s.p = nullptr;
+  s.bytes = 0;
+  CK(cudaMallocAsync(&s.p, bytes, h->st));
+  s.bytes = bytes;
+  return 0;
+}
+
+// env advance through site c.  right=0: new left env slot[c] from slot[c-1];
+// right=1: new right env slot[c] from slot[c+1].  (fixedL.cc:144-150, 221-229)
+int advance_env(tnml_handle h, int c, int right) {
+  Site& w = h->W[c];
+  if (!w.d) return fail(h, TNML_ERR_INVALID, "site tensor %d not set", c);
+  const long NT = h->NT;
+  const int prevc = right ? c + 1 : c - 1;
+  const bool hasPrev = (prevc >= 1 && prevc <= h->N);
+  EnvRef pe{h->ones, 1, 0};
+  if (hasPrev) {
+    Slot& ps = h->slot[prevc];
+    if (ps.kind != (right ? 2 : 1))
+      return fail(h, TNML_ERR_INVALID, "cannot advance env to site %d: slot %d not a %s env", c, prevc,
+                  right ? "right" : "left");
+    pe = {ps.p, ps.m, ps.fat};
+  }
+  const int kin = right ? w.mr : w.ml;    // contracted link
+  const int kout = right ? w.ml : w.mr;   // new env dim
+  if (pe.m != kin) return fail(h, TNML_ERR_INVALID, "env dim %d != link dim %d at site %d", pe.m, kin, c);
+  if (pe.fat && w.lab) return fail(h, TNML_ERR_INVALID, "two label indices at site %d", c);
+  const int outfat = (pe.fat || w.lab) ? 1 : 0;
+  Slot& ns = h->slot[c];
+  const size_t bytes = (size_t)NT * kout * (outfat ? NL : 1) * sizeof(double);
+  TRY(alloc_slot(h, ns, bytes));
+  const double* Bm = w.d;
+  PhaseTimer t(h, PH_SHIFT);
+  if (right || w.lab) {
+    TRY(ensure(h, h->Bm, (size_t)w.size()));
+    permute_site(h->st, w.d, w.ml, w.mr, w.lab ? NL : 1, right, h->Bm.p);
+    CKL();
+    h->stats.launches += 1;
+    Bm = h->Bm.p;
+  }
+  const long rows = pe.fat ? NT * NL : NT;
+  const int div = pe.fat ? NL : 1;
+  const int J = kout * (w.lab ? NL : 1);
+  krgemm(h->st, 1, pe.p, kin, kin, featp(h, c), div, Bm, nullptr, J, J, nullptr, ns.p, J, rows);
+  CKL();
+  h->stats.launches += 1;
+  h->stats.alg_flops += (double)rows * 4.0 * kin * J;
+  h->stats.alg_bytes += 8.0 * rows * ((double)kin + J);
+  ns.m = kout;
+  ns.fat = outfat;
+  ns.kind = right ? 2 : 1;
+  return 0;
+}
+
+int set_site_dev(tnml_handle h, int j, int ml, int mr, int lab) {
+  Site& s = h->W[j];
+  size_t n = (size_t)ml * 2 * mr * (lab ? NL : 1);
+  if (n > s.cap) {
+    if (s.d) CK(cudaFreeAsync(s.d, h->st));
+    s.d = nullptr;
+    s.cap = 0;
+    CK(cudaMallocAsync(&s.d, n * sizeof(double), h->st));
+    s.cap = n;
+  }
+  s.ml = ml;
+  s.mr = mr;
+  s.lab = lab;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* tnml_version(void) { return "tnml_b200 0.1 (sm_100a, float64, block-Jacobi SVD)"; }
+
+const char* tnml_last_error(tnml_handle h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int tnml_create(int device, int flags, tnml_handle* out) {
+  (void)flags;
+  if (!out) return fail(nullptr, TNML_ERR_INVALID, "out == NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, TNML_ERR_NODEVICE, "no CUDA device (%s); tnml_b200 has no CPU path",
+                e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, TNML_ERR_INVALID, "device %d out of range (%d)", device, ndev);
+  tnml_handle h = new tnml_handle_s();
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, TNML_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  h->num_sm = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, TNML_ERR_CUDA, "cudaStreamCreate failed");
+  }
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  h->nfat_blocks = fat_blocks(h->num_sm);
+  if (cudaMalloc(&h->stats_partial, (size_t)h->nfat_blocks * 16 * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&h->dscal, 64 * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&h->dot_scratch, 1024 * sizeof(double)) != cudaSuccess ||
+      cudaMallocHost(&h->hpin, 64 * sizeof(double)) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, TNML_ERR_CUDA, "workspace allocation failed");
+  }
+  *out = h;
+  return TNML_OK;
+}
+
+int tnml_destroy(tnml_handle h) {
+  if (!h) return TNML_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->st);
+  if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
+  for (auto& s : h->slot)
+    if (s.p) cudaFree(s.p);
+  for (auto& s : h->W)
+    if (s.d) cudaFree(s.d);
+  DBuf* bufs[] = {&h->B, &h->r, &h->p, &h->G, &h->T, &h->Gpart, &h->Q, &h->Z, &h->Bm};
+  for (DBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  void* ptrs[] = {h->feat, h->labels, h->ones, h->P, h->pred, h->stats_partial, h->dscal, h->dot_scratch,
+                  h->svd.X, h->svd.J, h->svd.sig2, h->svd.perm, h->svd.info, h->svd.flags};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (h->hpin) cudaFreeHost(h->hpin);
+  for (auto& e : h->evs) {
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  for (auto e : h->evpool) cudaEventDestroy(e);
+  cudaStreamDestroy(h->st);
+  delete h;
+  return TNML_OK;
+}
+
+int tnml_set_images(tnml_handle h, int64_t NT, int N, const double* feat, const int32_t* labels,
+                    int64_t NT_global, int64_t first) {
+  if (!h) return TNML_ERR_INVALID;
+  if (NT <= 0 || N < 4 || !feat || !labels) return fail(h, TNML_ERR_INVALID, "bad image set (NT=%ld N=%d)", (long)NT, N);
+  for (int64_t n = 0; n < NT; ++n)
+    if (labels[n] < 0 || labels[n] >= NL) return fail(h, TNML_ERR_INVALID, "label %d of image %ld out of range", labels[n], (long)n);
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->st));
+  for (auto& s : h->slot)
+    if (s.p) cudaFree(s.p);
+  for (auto& s : h->W)
+    if (s.d) cudaFree(s.d);
+  void* ptrs[] = {h->feat, h->labels, h->ones, h->P, h->pred};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  h->feat = nullptr, h->labels = nullptr, h->ones = nullptr, h->P = nullptr, h->pred = nullptr;
+  h->NT = NT;
+  h->NTg = NT_global > 0 ? NT_global : NT;
+  h->first = first;
+  h->N = N;
+  h->jc = N / 2;  // fixedL.cc:616
+  h->slot.assign(N + 2, Slot());
+  h->W.assign(N + 2, Site());
+  h->currb = -1;
+  h->bond_valid = false;
+  const size_t nf = (size_t)(N + 2) * NT * 2;
+  CK(cudaMalloc(&h->feat, nf * sizeof(double)));
+  CK(cudaMalloc(&h->labels, NT * sizeof(int32_t)));
+  CK(cudaMalloc(&h->ones, NT * sizeof(double)));
+  CK(cudaMalloc(&h->P, (size_t)NT * NL * sizeof(double)));
+  CK(cudaMalloc(&h->pred, NT * sizeof(int32_t)));
+  // [NT][N][2] -> [N+2][NT][2] (site-major: one bond's features are contiguous)
+  std::vector<double> stage(nf, 0.0);
+  for (int64_t n = 0; n < NT; ++n)
+    for (int j = 1; j <= N; ++j) {
+      const double* src = feat + ((size_t)n * N + (j - 1)) * 2;
+      double* dst = stage.data() + ((size_t)j * NT + n) * 2;
+      dst[0] = src[0];
+      dst[1] = src[1];
+    }
+  CK(cudaMemcpyAsync(h->feat, stage.data(), nf * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  CK(cudaMemcpyAsync(h->labels, labels, NT * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
+  fill(h->st, h->ones, NT, 1.0);
+  CKL();
+  CK(cudaStreamSynchronize(h->st));
+  return TNML_OK;
+}
+
+int tnml_set_site(tnml_handle h, int j, int ml, int mr, int has_label, const double* data) {
+  if (!h) return TNML_ERR_INVALID;
+  if (h->N == 0) return fail(h, TNML_ERR_INVALID, "tnml_set_images must be called first");
+  if (j < 1 || j > h->N || ml < 1 || mr < 1 || !data) return fail(h, TNML_ERR_INVALID, "bad site %d (%d,%d)", j, ml, mr);
+  if ((has_label != 0) != (j == h->jc)) return fail(h, TNML_ERR_INVALID, "Label Index not on site %d", h->jc);
+  CK(cudaSetDevice(h->device));
+  TRY(set_site_dev(h, j, ml, mr, has_label ? 1 : 0));
+  CK(cudaMemcpyAsync(h->W[j].d, data, (size_t)h->W[j].size() * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  if (j == h->currb || j == h->currb + 1) h->bond_valid = false;
+  return TNML_OK;
+}
+
+int tnml_get_site_dims(tnml_handle h, int j, int* ml, int* mr, int* has_label) {
+  if (!h || j < 1 || j > h->N || !h->W[j].d) return h ? fail(h, TNML_ERR_INVALID, "site %d not set", j) : TNML_ERR_INVALID;
+  if (ml) *ml = h->W[j].ml;
+  if (mr) *mr = h->W[j].mr;
+  if (has_label) *has_label = h->W[j].lab;
+  return TNML_OK;
+}
+
+int tnml_get_site(tnml_handle h, int j, double* data, size_t capacity_elems) {
+  if (!h || j < 1 || j > h->N || !h->W[j].d) return h ? fail(h, TNML_ERR_INVALID, "site %d not set", j) : TNML_ERR_INVALID;
+  size_t n = (size_t)h->W[j].size();
+  if (capacity_elems < n) return fail(h, TNML_ERR_INVALID, "buffer too small for site %d (%zu < %zu)", j, capacity_elems, n);
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(data, h->W[j].d, n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  return TNML_OK;
+}
+
+int tnml_init_envs(tnml_handle h) {
+  if (!h || h->N == 0) return h ? fail(h, TNML_ERR_INVALID, "no images") : TNML_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  for (int j = 1; j <= h->N; ++j)
+    if (!h->W[j].d) return fail(h, TNML_ERR_INVALID, "site tensor %d not set", j);
+  if (!h->W[h->jc].lab) return fail(h, TNML_ERR_INVALID, "Label Index not on site %d", h->jc);
+  for (auto& s : h->slot) s.kind = 0;
+  for (int n = h->N; n >= 3; --n) TRY(advance_env(h, n, 1));
+  h->currb = -1;
+  return tnml_set_bond(h, 1);
+}
+
+int tnml_set_bond(tnml_handle h, int b) {
+  if (!h) return TNML_ERR_INVALID;
+  if (b < 1 || b >= h->N) return fail(h, TNML_ERR_INVALID, "bond %d out of range", b);
+  if (h->currb == b) return TNML_OK;  // fixedL.cc:162
+  h->currb = b;
+  h->bond_valid = false;
+  return TNML_OK;
+}
+
+int tnml_bond_form(tnml_handle h) {
+  if (!h || h->currb < 1) return h ? fail(h, TNML_ERR_INVALID, "no current bond") : TNML_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  const int b = h->currb;
+  TRY(setup_geom(h, b));
+  const long n = h->g.size();
+  TRY(ensure(h, h->B, (size_t)n));
+  PhaseTimer t(h, PH_OTHER);
+  form_bond(h->st, h->W[b].d, h->W[b + 1].d, h->W[b].mr, h->g, h->B.p);
+  CKL();
+  h->stats.launches += 1;
+  h->bond_valid = true;
+  return TNML_OK;
+}
+
+int tnml_bond_dims(tnml_handle h, int* ml, int* mr, int* has_label) {
+  if (!h || !h->bond_valid) return h ? fail(h, TNML_ERR_INVALID, "no bond tensor formed") : TNML_ERR_INVALID;
+  if (ml) *ml = h->g.ml;
+  if (mr) *mr = h->g.mr;
+  if (has_label) *has_label = (h->g.nl == NL);
+  return TNML_OK;
+}
+
+int tnml_bond_load(tnml_handle h, const double* B, size_t n_elems) {
+  if (!h || h->currb < 1 || !B) return h ? fail(h, TNML_ERR_INVALID, "no current bond") : TNML_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  TRY(setup_geom(h, h->currb));
+  const long n = h->g.size();
+  if ((long)n_elems != n) return fail(h, TNML_ERR_INVALID, "bond tensor has %ld elements, got %zu", n, n_elems);
+  TRY(ensure(h, h->B, (size_t)n));
+  TRY(ensure(h, h->T, (size_t)n));
+  CK(cudaMemcpyAsync(h->T.p, B, n * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  bond_from_host_layout(h->st, h->T.p, h->g, h->B.p);
+  CKL();
+  CK(cudaStreamSynchronize(h->st));
+  h->bond_valid = true;
+  return TNML_OK;
+}
+
+int tnml_bond_store(tnml_handle h, double* B, size_t capacity_elems) {
+  if (!h || !h->bond_valid || !B) return h ? fail(h, TNML_ERR_INVALID, "no bond tensor formed") : TNML_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  const long n = h->g.size();
+  if ((long)capacity_elems < n) return fail(h, TNML_ERR_INVALID, "buffer too small for bond tensor");
+  TRY(ensure(h, h->T, (size_t)n));
+  bond_to_host_layout(h->st, h->B.p, h->g, h->T.p);
+  CKL();
+  CK(cudaMemcpyAsync(B, h->T.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  return TNML_OK;
+}
+
+int tnml_cgrad(tnml_handle h, int Npass, double lambda, double cconv, double* cost_per_pass,
+               double* rnorm_per_pass, int* npass_done) {
+  if (!h || !h->bond_valid) return h ? fail(h, TNML_ERR_INVALID, "no bond tensor formed") : TNML_ERR_INVALID;
+  if (Npass < 1) return fail(h, TNML_ERR_INVALID, "Npass must be >= 1");
+  CK(cudaSetDevice(h->device));
+  const long n = h->g.size();
+  TRY(ensure(h, h->r, (size_t)n));
+  TRY(ensure(h, h->p, (size_t)n));
+  double hs[16];
+  int nd = 0;
+  // r = sum_n (delta - B v_n) v_n - lambda B     (fixedL.cc:373-386)
+  TRY(grad_eval(h, h->B.p, hs));
+  CK(cudaMemcpyAsync(h->r.p, h->G.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  if (lambda != 0.0) {
+    axpby(h->st, n, -lambda, h->B.p, 1.0, h->r.p);
+    CKL();
+    h->stats.launches += 1;
+  }
+  CK(cudaMemcpyAsync(h->p.p, h->r.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->st));  // p = r (388)
+  double rr = 0.0;
+  TRY(ddot(h, n, h->r.p, h->r.p, &rr));
+  for (int pass = 1; pass <= Npass; ++pass) {
+    // pAp = sum_n |p v_n|^2 + lambda |p|^2          (393-403)
+    TRY(forward(h, h->p.p, FAT_PAP, h->dscal));
+    TRY(allreduce(h, h->dscal, 16));
+    TRY(fetch(h, h->dscal, 16, hs));
+    double pAp = hs[11];
+    if (lambda != 0.0) {
+      double pp = 0.0;
+      TRY(ddot(h, n, h->p.p, h->p.p, &pp));
+      pAp += lambda * pp;
+    }
+    const double a = rr / pAp;                        // 405
+    axpby(h->st, n, a, h->p.p, 1.0, h->B.p);          // 406
+    CKL();
+    h->stats.launches += 1;
+    if (pass == Npass) break;                         // 409
+    TRY(grad_eval(h, h->B.p, hs));                    // 412-421
+    if (lambda != 0.0) {
+      axpby(h->st, n, -lambda, h->B.p, 1.0, h->G.p);  // 422
+      CKL();
+      h->stats.launches += 1;
+    }
+    double nrr = 0.0;
+    TRY(ddot(h, n, h->G.p, h->G.p, &nrr));
+    const double beta = nrr / rr;                     // 423
+    CK(cudaMemcpyAsync(h->r.p, h->G.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->st));  // 424
+    rr = nrr;
+    double C = 0.0;
+    for (int l = 0; l < NL; ++l) C += hs[l];          // 427
+    if (lambda != 0.0) {
+      double bb = 0.0;
+      TRY(ddot(h, n, h->B.p, h->B.p, &bb));
+      C += lambda * bb;                               // 428
+    }
+    if (nd < 8) {
+      if (cost_per_pass) cost_per_pass[nd] = C / (double)h->NTg;  // 429
+      if (rnorm_per_pass) rnorm_per_pass[nd] = std::sqrt(rr);
+    }
+    ++nd;
+    if (std::sqrt(rr) < cconv) break;                 // 432-436
+    axpby(h->st, n, 1.0, h->r.p, beta, h->p.p);       // p = r + beta p (442)
+    CKL();
+    h->stats.launches += 1;
+  }
+  if (npass_done) *npass_done = nd;
+  return TNML_OK;
+}
+
+int tnml_svd_split(tnml_handle h, int dir, double cutoff, int maxm, int minm, int do_rel_cutoff, int* newm,
+                   double* truncerr) {
+  if (!h || !h->bond_valid) return h ? fail(h, TNML_ERR_INVALID, "no bond tensor formed") : TNML_ERR_INVALID;
+  if (dir != TNML_FROMLEFT && dir != TNML_FROMRIGHT) return fail(h, TNML_ERR_INVALID, "bad direction %d", dir);
+  if (maxm < 1) return fail(h, TNML_ERR_INVALID, "maxm must be >= 1");
+  CK(cudaSetDevice(h->device));
+  const int b = h->currb;
+  const BondGeom g = h->g;
+  const int nlA = g.lab_b ? NL : 1, nlB = g.lab_b1 ? NL : 1;
+  const int nA = 2 * g.ml * nlA, nB = 2 * g.mr * nlB;
+  const int keep = std::min(std::min(nA, nB), maxm);
+  // new buffers (the old site tensors are not inputs of the SVD: B is)
+  TRY(set_site_dev(h, b, g.ml, keep, g.lab_b));
+  TRY(set_site_dev(h, b + 1, keep, g.mr, g.lab_b1));
+  int m = 0, sweeps = 0;
+  double terr = 0.0;
+  int rc;
+  {
+    PhaseTimer t(h, PH_SVD);
+    rc = svd_split(h->st, h->svd, h->B.p, g, dir, cutoff, maxm, minm, do_rel_cutoff, h->W[b].d, h->W[b + 1].d, &m,
+                   &terr, &sweeps, (long*)&h->stats.launches);
+  }
+  if (rc == -2) return fail(h, TNML_ERR_CUDA, "svd kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (rc == -5) return fail(h, TNML_ERR_NOCONV, "Jacobi SVD did not converge in 40 sweeps");
+  h->W[b].mr = m;
+  h->W[b + 1].ml = m;
+  h->stats.alg_flops += 4.0 * std::max(nA, nB) * (double)std::min(nA, nB) * std::min(nA, nB);
+  h->hpin[32] = (double)sweeps;
+  if (newm) *newm = m;
+  if (truncerr) *truncerr = terr;
+  return TNML_OK;
+}
+
+int tnml_quadcost(tnml_handle h, int use_sites, double lambda, double* C, double* C_label, int64_t* ncorrect) {
+  if (!h || h->currb < 1) return h ? fail(h, TNML_ERR_INVALID, "no current bond") : TNML_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  const double* X;
+  if (use_sites) {
+    const int b = h->currb;
+    TRY(setup_geom(h, b));
+    TRY(ensure(h, h->T, (size_t)h->g.size()));
+    form_bond(h->st, h->W[b].d, h->W[b + 1].d, h->W[b].mr, h->g, h->T.p);
+    CKL();
+    h->stats.launches += 1;
+    X = h->T.p;
+  } else {
+    if (!h->bond_valid) return fail(h, TNML_ERR_INVALID, "no bond tensor formed");
+    X = h->B.p;
+  }
+  double hs[16];
+  TRY(forward(h, X, FAT_COST, h->dscal));
+  TRY(allreduce(h, h->dscal, 16));
+  TRY(fetch(h, h->dscal, 16, hs));
+  double c = 0.0;
+  for (int l = 0; l < NL; ++l) {
+    c += hs[l];
+    if (C_label) C_label[l] = hs[l];
+  }
+  if (lambda != 0.0) {
+    double bb = 0.0;
+    TRY(ddot(h, h->g.size(), X, X, &bb));
+    c += lambda * bb;  // fixedL.cc:329
+  }
+  if (C) *C = c;
+  if (ncorrect) *ncorrect = (int64_t)llround(hs[10]);
+  return TNML_OK;
+}
+
+int tnml_shift_env(tnml_handle h, int b, int dir) {
+  if (!h) return TNML_ERR_INVALID;
+  if (b < 1 || b >= h->N) return fail(h, TNML_ERR_INVALID, "bond %d out of range", b);
+  if (dir != TNML_FROMLEFT && dir != TNML_FROMRIGHT) return fail(h, TNML_ERR_INVALID, "bad direction %d", dir);
+  CK(cudaSetDevice(h->device));
+  const int c = (dir == TNML_FROMLEFT) ? b : b + 1;  // fixedL.cc:196
+  return advance_env(h, c, dir == TNML_FROMLEFT ? 0 : 1);
+}
+
+int tnml_bond_update(tnml_handle h, int b, int ha, const tnml_bond_params* p, tnml_bond_result* out) {
+  if (!h || !p) return TNML_ERR_INVALID;
+  if (ha != 1 && ha != 2) return fail(h, TNML_ERR_INVALID, "ha must be 1 or 2");
+  tnml_bond_result res;
+  memset(&res, 0, sizeof(res));
+  TRY(tnml_set_bond(h, b));                                            // 488
+  TRY(tnml_bond_form(h));                                              // 493-498
+  res.origm = h->W[b].mr;
+  TRY(tnml_cgrad(h, p->Npass, p->lambda, p->cconv, res.cg_cost, res.cg_rnorm, &res.npass_done));  // 504
+  const long n = h->g.size();
+  TRY(tnml_svd_split(h, ha == 1 ? TNML_FROMLEFT : TNML_FROMRIGHT, p->cutoff, p->maxm, p->minm, p->do_rel_cutoff,
+                     &res.newm, &res.truncerr));                        // 519-521
+  res.svd_sweeps = (int)h->hpin[32];
+  TRY(tnml_quadcost(h, 1, p->lambda, &res.cost, res.cost_label, &res.ncorrect));  // 527-532 (newB in T)
+  // |B|, |B - newB|  (528-530)
+  double bb = 0.0, dd = 0.0;
+  TRY(ddot(h, n, h->B.p, h->B.p, &bb));
+  axpby(h->st, n, -1.0, h->T.p, 1.0, h->B.p);
+  CKL();
+  h->stats.launches += 1;
+  TRY(ddot(h, n, h->B.p, h->B.p, &dd));
+  res.normB = std::sqrt(bb);
+  res.dB = std::sqrt(dd);
+  h->bond_valid = false;
+  TRY(tnml_shift_env(h, b, ha == 1 ? TNML_FROMLEFT : TNML_FROMRIGHT));  // 540
+  if (out) *out = res;
+  return TNML_OK;
+}
+
+int tnml_predict(tnml_handle h, int32_t* labels_out, double* P_out) {
+  if (!h || h->NT == 0) return h ? fail(h, TNML_ERR_INVALID, "no images") : TNML_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  if (labels_out) CK(cudaMemcpyAsync(labels_out, h->pred, h->NT * sizeof(int32_t), cudaMemcpyDeviceToHost, h->st));
+  if (P_out) CK(cudaMemcpyAsync(P_out, h->P, (size_t)h->NT * NL * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  return TNML_OK;
+}
+
+int tnml_get_env(tnml_handle h, int slot, int* m, int* is_fat, double* data, size_t capacity_elems) {
+  if (!h || slot < 1 || slot > h->N) return h ? fail(h, TNML_ERR_INVALID, "bad slot %d", slot) : TNML_ERR_INVALID;
+  Slot& s = h->slot[slot];
+  if (s.kind == 0) return fail(h, TNML_ERR_INVALID, "slot %d empty", slot);
+  if (m) *m = s.m;
+  if (is_fat) *is_fat = s.fat;
+  if (data) {
+    size_t n = (size_t)h->NT * s.m * (s.fat ? NL : 1);
+    if (capacity_elems < n) return fail(h, TNML_ERR_INVALID, "buffer too small for slot %d", slot);
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(data, s.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+  }
+  return TNML_OK;
+}
+
+int tnml_comm_get_unique_id(uint8_t* id) {
+  if (!id) return TNML_ERR_INVALID;
+  std::string err;
+  if (!load_nccl(err)) return fail(nullptr, TNML_ERR_NCCL, "%s", err.c_str());
+  NcclId uid;
+  int rc = g_nccl.get_uid(&uid);
+  if (rc != 0) return fail(nullptr, TNML_ERR_NCCL, "ncclGetUniqueId failed (%d)", rc);
+  memcpy(id, uid.internal, TNML_UNIQUE_ID_BYTES);
+  return TNML_OK;
+}
+
+int tnml_comm_init_rank(tnml_handle h, int nranks, int rank, const uint8_t* id) {
+  if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) return h ? fail(h, TNML_ERR_INVALID, "bad comm args") : TNML_ERR_INVALID;
+  std::string err;
+  if (!load_nccl(err)) return fail(h, TNML_ERR_NCCL, "%s", err.c_str());
+  CK(cudaSetDevice(h->device));
+  NcclId uid;
+  memcpy(uid.internal, id, TNML_UNIQUE_ID_BYTES);
+  void* comm = nullptr;
+  int rc = g_nccl.init_rank(&comm, nranks, uid, rank);
+  if (rc != 0) return fail(h, TNML_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
+  h->comm = comm;
+  h->nranks = nranks;
+  h->rank = rank;
+  return TNML_OK;
+}
+
+int tnml_get_stats(tnml_handle h, tnml_stats* out, int reset) {
+  if (!h) return TNML_ERR_INVALID;
+  cudaSetDevice(h->device);
+  drain_events(h);
+  if (out) *out = h->stats;
+  if (reset) memset(&h->stats, 0, sizeof(h->stats));
+  return TNML_OK;
+}
+
+int tnml_set_timing(tnml_handle h, int on) {
+  if (!h) return TNML_ERR_INVALID;
+  cudaSetDevice(h->device);
+  drain_events(h);
+  h->timing = (on != 0);
+  return TNML_OK;
+}
+
+int tnml_synchronize(tnml_handle h) {
+  if (!h) return TNML_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->st));
+  return TNML_OK;
+}
+
+void* tnml_stream(tnml_handle h) { return h ? (void*)h->st : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// tnml_kernels.cuh -- launch wrappers of the sm_100a kernels behind the C-ABI.
+// All arithmetic is float64: the reference computes in ITensor `Real` = double
+// and the CG of fixedL.cc:349-445 is too ill-conditioned for less (DESIGN.md
+// "Precision").
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace tnml {
+
+constexpr int NL = 10;
+
+// ---- Khatri-Rao GEMM family -------------------------------------------------
+// krgemm: Out[row][j] = sum_q w_q(row) * sum_{a,s} In[row][a]*f1[img(row)][s] * Bm_q[(a*2+s)*ldb + j]
+//   img(row) = row / div ; NB = 1: w_0 = 1 ; NB = 2: w_q = f2[img(row)*2+q]
+// Used for: projected input Q (fixedL.cc:318,377,399,416 restructured) and
+// environment advance (fixedL.cc:144-150, 221-229).
+void krgemm(cudaStream_t st, int NB, const double* In, long ldin, int ma, const double* f1, int div,
+            const double* Bm0, const double* Bm1, long ldb, int J, const double* f2, double* Out,
+            long ldout, long rows);
+
+// krgram: Gpart[split][(a*2+s)][q][j] = sum_{row in split} In[row][a]*f1[row][s]*f2[row][q]*Z[row][j]
+// (NB = 1: f2 == nullptr, weight 1).  The rank-1 gradient accumulation of
+// fixedL.cc:379,418 as one K=NT contraction, split-K over CTAs, partials
+// reduced in a fixed order (deterministic).  Returns the number of splits.
+int krgram_splits(int ma, int J, int NB, long rows, int num_sm);
+void krgram(cudaStream_t st, int NB, const double* In, long ldin, int ma, const double* f1,
+            const double* f2, const double* Z, long ldz, int J, double* Gpart, long rows, int nsplit);
+// G[i] = sum_split Gpart[split][i]   (+ optional: G[i] -= lambda*B[i])
+void reduce_partials(cudaStream_t st, const double* Gpart, int nsplit, long n, double* G);
+
+// ---- fat-environment kernel -------------------------------------------------
+// One warp per image.  P[n][l] = sum_f Q[n][f]*F[n][l][f].
+enum FatMode : int {
+  FAT_GRAD = 0,   // dP = delta_{label} - P ; stats ; Z[n][f] = sum_l dP[l]*F[n][l][f]
+  FAT_PAP = 1,    // stats[11] += sum_l P[l]^2
+  FAT_COST = 2,   // stats (cost per label, ncorrect), pred
+  FAT_GRAD_OUTER = 3,  // class C: Zfat[n][l][f] = dP[l]*Q[n][f]
+};
+// stats layout (double[16]): [0..9] cost per label, [10] ncorrect, [11] sum |P|^2
+void fat_kernel(cudaStream_t st, int mode, const double* Q, const double* F, int m, const int32_t* labels,
+                double* P, double* Z, int32_t* pred, double* stats_partial, int nblocks, long NT);
+int fat_blocks(int num_sm);
+void reduce_stats(cudaStream_t st, const double* stats_partial, int nblocks, double* stats /*[16]*/);
+
+// ---- small dense tensor helpers ---------------------------------------------
+// geometry of a bond-shaped tensor in its device ("canonical") layout
+struct BondGeom {
+  int ml, mr, nl;          // nl = 1 or NL
+  int lab_b, lab_b1;       // label on site b / on site b+1
+  long sa, ss, st, sb, sl; // strides of (alpha, s, t, beta, label)
+  __host__ __device__ long size() const { return (long)ml * 4 * mr * nl; }
+};
+// B[alpha,s,t,beta(,l)] = sum_m Wb[alpha,s,m(,l)] * Wb1[m,t,beta(,l)]   (fixedL.cc:494)
+void form_bond(cudaStream_t st, const double* Wb, const double* Wb1, int m, BondGeom g, double* B);
+// host layout [ml][2][2][mr][nl] <-> canonical
+void bond_to_host_layout(cudaStream_t st, const double* Bc, BondGeom g, double* Bh);
+void bond_from_host_layout(cudaStream_t st, const double* Bh, BondGeom g, double* Bc);
+
+// site tensor W[a][s][b](,[l]) -> GEMM operand for an environment advance:
+//  left : Bm[(a*2+s)][(l*mb + b)]  = W[a][s][b][l]
+//  right: Bm[(b*2+s)][(l*ma + a)]  = W[a][s][b][l]
+void permute_site(cudaStream_t st, const double* W, int ma, int mb, int nl, int right, double* Bm);
+
+void fill(cudaStream_t st, double* x, long n, double v);
+// y = a*x + b*y
+void axpby(cudaStream_t st, long n, double a, const double* x, double b, double* y);
+// out[0] = sum x*y (deterministic two-stage)
+void dot(cudaStream_t st, long n, const double* x, const double* y, double* scratch, double* out);
+
+// ---- truncated SVD (tnml_svd.cu) ----------------------------------------------
+struct SvdWork {
+  double* X = nullptr;     // [small][big]  column-major working matrix (columns = "small" index)
+  double* J = nullptr;     // [small][small] accumulated rotations
+  double* sig2 = nullptr;  // [small]
+  int* perm = nullptr;     // [small]
+  double* info = nullptr;  // [8]: 0 maxoff of last sweep, 1 newm, 2 truncerr, 3 sweeps, 4 sum sig2
+  int* flags = nullptr;    // [4]: 0 converged
+  long capX = 0, capJ = 0;
+  int capS = 0;
+};
+// Gather canonical B into X (tall orientation), run block one-sided Jacobi,
+// sort, apply ITensor's truncation rule, scatter U -> W(c), S*V -> W(c+dc).
+// dir = 1: rows are (alpha,s[,l]) ; dir = 2: rows are (t,beta[,l]).
+// Wb_out / Wb1_out must hold 2*ml*maxkeep*nl and maxkeep*2*mr*nl doubles.
+// Returns (via host sync) newm, truncerr, sweeps.
+int svd_split(cudaStream_t st, SvdWork& w, const double* Bc, BondGeom g, int dir, double cutoff, int maxm,
+              int minm, int do_rel_cutoff, double* Wb_out, double* Wb1_out, int* newm, double* truncerr,
+              int* sweeps, long* launches);
+
+}  // namespace tnml

@@ -1,0 +1,343 @@
+// tnml_svd.cu -- truncated SVD of the bond tensor on the device, float64.
+// Replaces ITensor's svd(B,U,S,V,{Cutoff,Maxm,Minm}) + `W.Aref(c+dc) *= S`
+// (fixedL.cc:519-521).
+//
+// Method: block one-sided (Hestenes) Jacobi.  The bond matrix is held in its
+// tall orientation X[small][big] (column-major, columns = the smaller index
+// set, at most 2*maxm of them); pairs of columns are rotated until mutually
+// orthogonal, the same rotations accumulate in J.  Columns are grouped in
+// blocks of 16: one "diagonal" launch orthogonalises the pairs inside every
+// block, then a round-robin tournament over block pairs (one CTA per block
+// pair, one warp per column pair, 16 inner rounds) covers the cross pairs.
+// Dot products are warp-shuffle reductions.  One-sided Jacobi is accurate for
+// small singular values in the relative sense, which matters because Minm
+// (fixedL.cc:593) forces the trailing vectors to be kept.
+#include "tnml_kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+
+namespace tnml {
+
+constexpr int JW = 16;  // block width (columns)
+
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// rotate columns ci, cj of X (length nb) and of J (length ns); returns |cos angle|
+__device__ __forceinline__ double rotate_pair(double* __restrict__ X, double* __restrict__ J, int nb, int ns,
+                                              int ci, int cj, double tol, int lane) {
+  if (ci >= ns || cj >= ns) return 0.0;
+  double* xi = X + (long)ci * nb;
+  double* xj = X + (long)cj * nb;
+  double a = 0.0, b = 0.0, g = 0.0;
+  for (int r = lane; r < nb; r += 32) {
+    double u = xi[r], v = xj[r];
+    a = fma(u, u, a);
+    b = fma(v, v, b);
+    g = fma(u, v, g);
+  }
+  a = wsum(a);
+  b = wsum(b);
+  g = wsum(g);
+  double den = sqrt(a) * sqrt(b);
+  if (!(den > 0.0)) return 0.0;
+  double off = fabs(g) / den;
+  if (off <= tol) return off;
+  double zeta = (b - a) / (2.0 * g);
+  double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  double c = 1.0 / sqrt(1.0 + t * t);
+  double s = c * t;
+  for (int r = lane; r < nb; r += 32) {
+    double u = xi[r], v = xj[r];
+    xi[r] = c * u - s * v;
+    xj[r] = s * u + c * v;
+  }
+  double* ji = J + (long)ci * ns;
+  double* jj = J + (long)cj * ns;
+  for (int r = lane; r < ns; r += 32) {
+    double u = ji[r], v = jj[r];
+    ji[r] = c * u - s * v;
+    jj[r] = s * u + c * v;
+  }
+  return off;
+}
+
+__device__ __forceinline__ void atomic_max_pos(double* addr, double v) {
+  // v >= 0: IEEE order == integer order
+  atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// circle-method round robin for n (even) players: pair k of round r
+__device__ __forceinline__ void rr_pair(int n, int r, int k, int& p, int& q) {
+  if (k == 0) {
+    p = n - 1;
+    q = r;
+  } else {
+    p = (r + k) % (n - 1);
+    q = (r - k + (n - 1)) % (n - 1);
+  }
+}
+
+// pairs inside each block of JW columns: 15 rounds x 8 pairs, 8 warps
+__global__ void __launch_bounds__(256)
+jacobi_diag_kernel(double* __restrict__ X, double* __restrict__ J, int nb, int ns, double tol,
+                   double* __restrict__ info, const int* __restrict__ flags) {
+  if (flags[0]) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * JW;
+  double mo = 0.0;
+  for (int r = 0; r < JW - 1; ++r) {
+    int p, q;
+    rr_pair(JW, r, warp, p, q);
+    double off = rotate_pair(X, J, nb, ns, c0 + p, c0 + q, tol, lane);
+    mo = fmax(mo, off);
+    __syncthreads();
+  }
+  if (lane == 0 && mo > 0.0) atomic_max_pos(info, mo);
+}
+
+// cross pairs of block pair (P,Q) chosen by outer round R: 16 rounds x 16 pairs, 16 warps
+__global__ void __launch_bounds__(512)
+jacobi_offdiag_kernel(double* __restrict__ X, double* __restrict__ J, int nb, int ns, int nblk_e, int R,
+                      double tol, double* __restrict__ info, const int* __restrict__ flags) {
+  if (flags[0]) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int P, Q;
+  rr_pair(nblk_e, R, blockIdx.x, P, Q);
+  double mo = 0.0;
+  for (int r = 0; r < JW; ++r) {
+    int ci = P * JW + warp;
+    int cj = Q * JW + ((warp + r) & (JW - 1));
+    double off = rotate_pair(X, J, nb, ns, ci, cj, tol, lane);
+    mo = fmax(mo, off);
+    __syncthreads();
+  }
+  if (lane == 0 && mo > 0.0) atomic_max_pos(info, mo);
+}
+
+__global__ void jacobi_sweep_end_kernel(double* __restrict__ info, int* __restrict__ flags, double tol) {
+  if (threadIdx.x == 0 && !flags[0]) {
+    info[3] += 1.0;
+    info[5] = info[0];
+    if (info[0] <= tol) flags[0] = 1;
+    info[0] = 0.0;
+  }
+}
+
+__global__ void svd_init_kernel(double* __restrict__ J, int ns, double* __restrict__ info, int* __restrict__ flags) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long n = (long)ns * ns;
+  if (idx < n) J[idx] = ((idx / ns) == (idx % ns)) ? 1.0 : 0.0;
+  if (idx < 8) info[idx] = 0.0;
+  if (idx < 4) flags[idx] = 0;
+}
+
+struct SvdGeom {
+  BondGeom g;
+  int nlA, nlB;  // label multiplicity on side A (site b) / side B (site b+1)
+  int nA, nB;    // 2*ml*nlA, 2*mr*nlB
+  int bigIsA;    // X columns are indexed by the small side, rows by the big side
+  int nb, ns;
+};
+
+__device__ __forceinline__ double bond_elem(const double* __restrict__ Bc, const SvdGeom& sg, int ia, int ib) {
+  int la = ia % sg.nlA, as = ia / sg.nlA;
+  int lb = ib % sg.nlB, tb = ib / sg.nlB;
+  int s = as & 1, a = as >> 1;
+  int b = tb % sg.g.mr, t = tb / sg.g.mr;
+  int l = (sg.nlA > 1) ? la : lb;
+  return Bc[a * sg.g.sa + s * sg.g.ss + t * sg.g.st + b * sg.g.sb + l * sg.g.sl];
+}
+
+__global__ void svd_gather_kernel(const double* __restrict__ Bc, SvdGeom sg, double* __restrict__ X) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long n = (long)sg.nb * sg.ns;
+  if (idx >= n) return;
+  int r = (int)(idx % sg.nb);
+  int c = (int)(idx / sg.nb);
+  int ia = sg.bigIsA ? r : c;
+  int ib = sg.bigIsA ? c : r;
+  X[idx] = bond_elem(Bc, sg, ia, ib);
+}
+
+// sigma^2, sort (descending, stable), ITensor truncation rule.  One CTA.
+__global__ void __launch_bounds__(1024)
+svd_finalize_kernel(const double* __restrict__ X, int nb, int ns, double* __restrict__ sig2,
+                    int* __restrict__ perm, double cutoff, int maxm, int minm, int do_rel,
+                    double* __restrict__ info) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = warp; c < ns; c += 32) {
+    const double* x = X + (long)c * nb;
+    double a = 0.0;
+    for (int r = lane; r < nb; r += 32) a = fma(x[r], x[r], a);
+    a = wsum(a);
+    if (lane == 0) sig2[c] = a;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < ns; c += blockDim.x) {
+    double v = sig2[c];
+    int rank = 0;
+    for (int k = 0; k < ns; ++k) {
+      double u = sig2[k];
+      rank += (u > v || (u == v && k < c)) ? 1 : 0;
+    }
+    perm[rank] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // ASSUMED ITensor v2 `truncate`; mirrors oracle.truncate_spectrum
+    int m = ns;
+    double terr = 0.0;
+    while (m > maxm) {
+      terr += sig2[perm[m - 1]];
+      --m;
+    }
+    double scale = 1.0;
+    if (do_rel) {
+      double s = 0.0;
+      for (int k = 0; k < ns; ++k) s += sig2[perm[k]];
+      scale = (s == 0.0) ? 1.0 : s;
+    }
+    while (m > minm && m > 1 && terr + sig2[perm[m - 1]] < cutoff * scale) {
+      terr += sig2[perm[m - 1]];
+      --m;
+    }
+    info[1] = (double)m;
+    info[2] = terr / scale;
+  }
+}
+
+// iso side gets unit vectors, the other side sigma * unit vectors
+__global__ void svd_scatter_kernel(const double* __restrict__ X, const double* __restrict__ J,
+                                   const double* __restrict__ sig2, const int* __restrict__ perm, SvdGeom sg,
+                                   int isoIsA, int m, double* __restrict__ Wb, double* __restrict__ Wb1) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long nAm = (long)sg.nA * m, nBm = (long)sg.nB * m;
+  if (idx >= nAm + nBm) return;
+  const bool sideA = idx < nAm;
+  long e = sideA ? idx : idx - nAm;
+  int k, i;  // kept vector index, index on this side
+  if (sideA) {  // W_b[as][k][l] : e = (as*m + k)*nlA + l
+    int l = (int)(e % sg.nlA);
+    long r = e / sg.nlA;
+    k = (int)(r % m);
+    int as = (int)(r / m);
+    i = as * sg.nlA + l;
+  } else {  // W_{b+1}[k][tb][l] : e = k*nB + ib
+    k = (int)(e / sg.nB);
+    i = (int)(e % sg.nB);
+  }
+  const int c = perm[k];
+  const bool thisIsBig = (sideA == (sg.bigIsA != 0));
+  const bool thisIsIso = (sideA == (isoIsA != 0));
+  double v = thisIsBig ? X[(long)c * sg.nb + i] : J[(long)c * sg.ns + i];
+  // X-type carries sigma, J-type is a unit vector
+  if (thisIsIso && thisIsBig) {
+    double sg1 = sqrt(sig2[c]);
+    v = (sg1 > 0.0) ? v / sg1 : 0.0;
+  } else if (!thisIsIso && !thisIsBig) {
+    v *= sqrt(sig2[c]);
+  }
+  if (sideA)
+    Wb[e] = v;
+  else
+    Wb1[e] = v;
+}
+
+static int ensure(SvdWork& w, long nX, int ns) {
+  if (nX > w.capX) {
+    if (w.X) cudaFree(w.X);
+    if (cudaMalloc(&w.X, nX * sizeof(double)) != cudaSuccess) return -1;
+    w.capX = nX;
+  }
+  long nJ = (long)ns * ns;
+  if (nJ > w.capJ) {
+    if (w.J) cudaFree(w.J);
+    if (cudaMalloc(&w.J, nJ * sizeof(double)) != cudaSuccess) return -1;
+    w.capJ = nJ;
+  }
+  if (ns > w.capS) {
+    if (w.sig2) cudaFree(w.sig2);
+    if (w.perm) cudaFree(w.perm);
+    if (cudaMalloc(&w.sig2, ns * sizeof(double)) != cudaSuccess) return -1;
+    if (cudaMalloc(&w.perm, ns * sizeof(int)) != cudaSuccess) return -1;
+    w.capS = ns;
+  }
+  if (!w.info) {
+    if (cudaMalloc(&w.info, 8 * sizeof(double)) != cudaSuccess) return -1;
+    if (cudaMalloc(&w.flags, 4 * sizeof(int)) != cudaSuccess) return -1;
+  }
+  return 0;
+}
+
+int svd_split(cudaStream_t st, SvdWork& w, const double* Bc, BondGeom g, int dir, double cutoff, int maxm,
+              int minm, int do_rel_cutoff, double* Wb_out, double* Wb1_out, int* newm, double* truncerr,
+              int* sweeps, long* launches) {
+  SvdGeom sg;
+  sg.g = g;
+  sg.nlA = g.lab_b ? NL : 1;
+  sg.nlB = g.lab_b1 ? NL : 1;
+  sg.nA = 2 * g.ml * sg.nlA;
+  sg.nB = 2 * g.mr * sg.nlB;
+  sg.bigIsA = (sg.nA >= sg.nB) ? 1 : 0;
+  sg.nb = sg.bigIsA ? sg.nA : sg.nB;
+  sg.ns = sg.bigIsA ? sg.nB : sg.nA;
+  const int ns = sg.ns, nb = sg.nb;
+  if (ensure(w, (long)nb * ns, ns) != 0) return -2;
+  long nl = 0;
+
+  long nJ = (long)ns * ns;
+  long ninit = nJ > 8 ? nJ : 8;
+  svd_init_kernel<<<(unsigned)((ninit + 255) / 256), 256, 0, st>>>(w.J, ns, w.info, w.flags);
+  long nX = (long)nb * ns;
+  svd_gather_kernel<<<(unsigned)((nX + 255) / 256), 256, 0, st>>>(Bc, sg, w.X);
+  nl += 2;
+
+  const double tol = std::sqrt((double)nb) * 1.1102230246251565e-16;
+  const int nblk = (ns + JW - 1) / JW;
+  const int nblk_e = (nblk % 2) ? nblk + 1 : nblk;
+  const int max_sweeps = 40;
+  int hflag = 0;
+  int done_sweeps = 0;
+  for (int sw = 0; sw < max_sweeps && !hflag; ++sw) {
+    jacobi_diag_kernel<<<nblk, 256, 0, st>>>(w.X, w.J, nb, ns, tol, w.info, w.flags);
+    nl += 1;
+    if (nblk_e >= 2 && nblk > 1) {
+      for (int R = 0; R < nblk_e - 1; ++R) {
+        jacobi_offdiag_kernel<<<nblk_e / 2, 512, 0, st>>>(w.X, w.J, nb, ns, nblk_e, R, tol, w.info, w.flags);
+        nl += 1;
+      }
+    }
+    jacobi_sweep_end_kernel<<<1, 32, 0, st>>>(w.info, w.flags, tol);
+    nl += 1;
+    done_sweeps = sw + 1;
+    if (sw >= 3 || nblk == 1) {  // first possible convergence checks are cheap relative to a sweep
+      if (cudaMemcpyAsync(&hflag, w.flags, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
+      if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
+    }
+  }
+  svd_finalize_kernel<<<1, 1024, 0, st>>>(w.X, nb, ns, w.sig2, w.perm, cutoff, maxm, minm, do_rel_cutoff, w.info);
+  nl += 1;
+  double hinfo[8];
+  if (cudaMemcpyAsync(hinfo, w.info, sizeof(hinfo), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
+  if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
+  const int m = (int)hinfo[1];
+  *newm = m;
+  *truncerr = hinfo[2];
+  *sweeps = (int)hinfo[3];
+  (void)done_sweeps;
+  const int isoIsA = (dir == 1) ? 1 : 0;
+  long nout = (long)(sg.nA + sg.nB) * m;
+  svd_scatter_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(w.X, w.J, w.sig2, w.perm, sg, isoIsA, m,
+                                                                    Wb_out, Wb1_out);
+  nl += 1;
+  if (launches) *launches += nl;
+  if (cudaGetLastError() != cudaSuccess) return -2;
+  return hflag ? 0 : -5;
+}
+
+}  // namespace tnml
