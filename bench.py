@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- bond-updates/sec of the fixedL hot path on B200 (BASELINE.json metric).
+
+One "step" = one iteration of the mldmrg loop body (fixedL.cc:478-563):
+setBond + cgrad(Npass=4) + svd + quadcost(newB) + shiftE, on BASELINE config 3
+shapes: synthetic MNIST-shaped 14x14 images (N=196 sites, d=2, 10 labels),
+NT=60000 images in total, maxm=120 (minm=60), cutoff 1e-10, float64.  With
+--gpus N the 60000 images are sharded over N ranks like ParallelDo bounds
+(BASELINE config 4, strong scaling) and the gradient is all-reduced by NCCL.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nt", type=int, default=60000, help="total training images (config 3: 60000)")
+    ap.add_argument("--maxm", type=int, default=120)
+    ap.add_argument("--npass", type=int, default=4)
+    ap.add_argument("--first-bond", type=int, default=10)
+    ap.add_argument("--cpu-sample", type=int, default=192, help="images in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.stop = False
+        self.idx = gpu_index
+        self.t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def start(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def finish(self):
+        self.stop = True
+        if self.t:
+            self.t.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def build_workload(args, rank, world):
+    """Synthetic config-3 shaped inputs for this rank's shard."""
+    from tnml_b200 import data, fixedl
+    NTg = args.nt
+    b0, b1 = fixedl.bounds(world, NTg)[rank]
+    pix, labels = data.synthetic_digits(b1 - b0, 14, seed=20260925, first=b0)
+    feat = data.phi(pix)                      # [NT, 196, 2] = TState::data
+    W = data.random_mps(196, 2, args.maxm, seed=3)
+    return feat, labels, W, NTg, b0
+
+
+def cpu_baseline(args, steps=1):
+    """The reference's CPU formulation (dense t.v, fixedL.cc:183-185,349-445)
+    timed on this box's host cores on a bounded sample of the workload."""
+    from oracle import fixedl_oracle as O           # checker / baseline only
+    from tnml_b200 import data
+    ns = args.cpu_sample
+    pix, labels = data.synthetic_digits(ns, 14, seed=20260925)
+    feat = O.features(pix)
+    W = data.random_mps(196, 2, args.maxm, seed=3)
+    ts = O.TrainStates(feat, labels.astype(np.int64), 1)
+    ts.init(W)
+    b = args.first_bond
+    for bb in range(1, b):
+        ts.set_bond(bb)
+        ts.shiftE(W, bb, "Fromleft")
+    minm = max(10, args.maxm // 2)
+    ts_per_step = []
+    for k in range(steps):
+        t0 = time.perf_counter()
+        ts.set_bond(b + k)
+        oB = O.form_bond(W[b + k], W[b + k + 1])
+        B, _, _ = O.cgrad(oB, ts, args.npass, 0.0, 1e-10, literal=True)
+        Wb, Wb1, m, te = O.svd_split(B, b + k, 1, ts.jc, args.maxm, minm, 1e-10)
+        W[b + k], W[b + k + 1] = Wb, Wb1
+        O.quadcost(O.form_bond(Wb, Wb1), ts, 0.0, literal=True)
+        ts.shiftE(W, b + k, "Fromleft")
+        ts_per_step.append(time.perf_counter() - t0)
+    t = float(np.mean(ts_per_step))
+    # per-image work is linear in NT (the SVD is NT independent and negligible here)
+    bonds_per_s = 1.0 / (t * args.nt / ns)
+    try:
+        import threadpoolctl
+        cores = max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] + [1])
+    except Exception:
+        cores = os.cpu_count() or 1
+    return {"value": bonds_per_s, "unit": "bond-updates/sec", "cores": int(cores), "kind": "port",
+            "sample": f"{ns} images x {steps} bond update(s) at ml=mr={args.maxm} (dense t.v literal numpy port of "
+                      f"fixedL.cc, float64), {t:.2f} s each, scaled linearly to NT={args.nt}",
+            "host_cpus": os.cpu_count()}, t
+
+
+def config_dict(args, world):
+    return {"workload": "BASELINE config 3/4: synthetic 14x14 MNIST-shaped, N=196 sites d=2 NL=10, "
+                        f"NT={args.nt} images total, maxm={args.maxm} minm={max(10, args.maxm // 2)} "
+                        f"Npass={args.npass} cutoff=1e-10, bonds {args.first_bond}.. (class L, ml=mr={args.maxm})",
+            "NT_total": args.nt, "N": 196, "maxm": args.maxm, "Npass": args.npass,
+            "parallelism": f"dp{world} (images sharded, NCCL all-reduce of the bond gradient)" if world > 1 else "dp1",
+            "l2": "per-bond inputs (environment cache, >=600 MB/rank at NT=60000) exceed the 126 MB L2; no flush needed"}
+
+
+# ---------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, t = cpu_baseline(args, steps=max(1, min(args.steps, 2)))
+    line = {"impl": "reference", "metric": "bond-updates/sec", "value": base["value"], "unit": "bond-updates/sec",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 / base["value"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, 1),
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "bond-updates/sec", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "images_bonds_per_sec": base["value"] * args.nt}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from tnml_b200 import capi, fixedl
+    feat, labels, W, NTg, first = build_workload(args, rank, world)
+    t_setup0 = time.perf_counter()
+    h = capi.Handle(local)
+    h.set_images(feat, labels, NTg, first)
+    h.set_mps(W)
+    if world > 1:
+        uid = torch.zeros(capi.UNIQUE_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.tensor(list(capi.comm_get_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        h.comm_init_rank(world, rank, bytes(uid.cpu().tolist()))
+    h.init_envs()
+    b0 = args.first_bond
+    for bb in range(1, b0):                     # left envs up to the first timed bond
+        h.set_bond(bb)
+        h.shift_env(bb, capi.FROMLEFT)
+    h.synchronize()
+    setup_s = time.perf_counter() - t_setup0
+
+    minm = max(10, args.maxm // 2)
+    p = capi.BondParams(args.npass, 0.0, 1e-10, 1e-10, args.maxm, minm, 0)
+    ext = torch.cuda.ExternalStream(h.stream(), device=torch.device("cuda", local))
+
+    def barrier():
+        h.synchronize()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, b_start, e2e=False):
+        """K bond updates; device time by CUDA events on the library's stream."""
+        res = []
+        h2d = d2h = 0
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ext):
+            ev0.record()
+        for k in range(nsteps):
+            b = b_start + k
+            if e2e:   # the host owns the MPS (like the reference's `W`): sites go H2D, results D2H
+                for j in (b, b + 1):
+                    h.set_site(j, Whost[j])
+                    h2d += Whost[j].nbytes
+            r = h.bond_update(b, 1, p)
+            if e2e:
+                for j in (b, b + 1):
+                    Whost[j] = h.get_site(j)
+                    d2h += Whost[j].nbytes
+                d2h += 8 * 40
+            res.append(r)
+        with torch.cuda.stream(ext):
+            ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, res, h2d, d2h
+
+    K, Wm = args.steps, max(args.warmup, 3)
+    ms, _, _, _ = timed(Wm, b0)                       # warm-up
+    b = b0 + Wm
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    h.stats(reset=True)
+    ms, res, _, _ = timed(K, b)
+    st = h.stats(reset=True)
+    clocks = sampler.finish() if rank == 0 else None
+    b += K
+    value = K / (ms / 1000.0)
+
+    # breakdown pass with per-phase CUDA events (on the library's stream)
+    h.set_timing(True)
+    ms_t, res_t, _, _ = timed(K, b)
+    stt = h.stats(reset=True)
+    h.set_timing(False)
+    b += K
+
+    # end-to-end pass: host-resident MPS, site tensors cross PCIe every step
+    Whost = {j: None for j in range(1, 197)}
+    for j in range(b, b + K + 2):
+        Whost[j] = h.get_site(j)
+    ms_e, res_e, h2d, d2h = timed(K, b, e2e=True)
+    e2e_value = K / (ms_e / 1000.0)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        NT = feat.shape[0]
+        m = args.maxm
+        # dominant phases, from the CUDA-event breakdown
+        phases = {"proj(krgemm)": stt.ms_proj, "grad(krgram)": stt.ms_grad, "fat": stt.ms_fat,
+                  "svd": stt.ms_svd, "shift": stt.ms_shift, "other": stt.ms_other}
+        tot = sum(phases.values())
+        dom = max(phases, key=phases.get)
+        npass = args.npass
+        n_fwd = (2 * npass + 1) * K          # forward passes (krgemm + fat) in K bond updates
+        n_bwd = npass * K
+        # algorithmic bytes per launch (float64): fat kernel reads Q + fat env (+ writes Z on gradient passes)
+        fat_bytes = 8.0 * NT * (m + 10 * m + 1) * n_fwd + 8.0 * NT * m * n_bwd
+        fat_gbs = fat_bytes / (stt.ms_fat / 1000.0) / 1e9 if stt.ms_fat > 0 else 0.0
+        gemm_flops = 8.0 * NT * m * m * (n_fwd + n_bwd)
+        gemm_tf = gemm_flops / ((stt.ms_proj + stt.ms_grad) / 1000.0) / 1e12 if stt.ms_proj > 0 else 0.0
+        roof = {"bound": "hbm", "kernel": "fat_kernel_t (label-carrying environment stream)",
+                "achieved": fat_gbs, "peak": peak, "unit": "GB/s", "frac": fat_gbs / peak, "traffic": None,
+                "peak_source": peak_src,
+                "launch_avg_ms": stt.ms_fat / max(1, n_fwd),
+                "phase_ms_per_step": {k: v / K for k, v in phases.items()}, "dominant_phase": dom,
+                "fp64_gemm": {"achieved_tflops": gemm_tf, "peak_tflops_nominal": 40.0,
+                              "frac": gemm_tf / 40.0,
+                              "note": "krgemm/krgram are FP64-FMA bound (no FP64 tcgen05 kind exists); "
+                                      "MEASURED_PEAKS.json has no FP64 figure, nominal B200 FP64 = 40 TF/s"}}
+        line = {"metric": "bond-updates/sec", "value": value, "unit": "bond-updates/sec", "n_gpus": world,
+                "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, world),
+                "images_bonds_per_sec": value * NTg,
+                "e2e": {"value": e2e_value, "unit": "bond-updates/sec", "h2d_bytes_per_step": h2d / K,
+                        "d2h_bytes_per_step": d2h / K,
+                        "note": "host-resident MPS: W(b),W(b+1) H2D before and D2H after every bond update "
+                                "through the C-ABI; images/environments are resident state (TrainStates)"},
+                "gpu_launches": int(st.launches), "clocks": clocks, "roofline": roof,
+                "setup_s": setup_s, "newm": [int(r.newm) for r in res][:8],
+                "svd_sweeps": [int(r.svd_sweeps) for r in res][:8],
+                "cost_per_image": [r.cost / NTg for r in res][:4]}
+        if not args.no_cpu_baseline:
+            base, _ = cpu_baseline(args, steps=1)
+            line["cpu_baseline"] = base
+        print(json.dumps(line))
+    h.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

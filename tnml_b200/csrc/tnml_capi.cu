@@ -802,7 +802,7 @@ int tnml_svd_split(tnml_handle h, int dir, double cutoff, int maxm, int minm, in
                    &terr, &sweeps, (long*)&h->stats.launches);
   }
   if (rc == -2) return fail(h, TNML_ERR_CUDA, "svd kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
-  if (rc == -5) return fail(h, TNML_ERR_NOCONV, "Jacobi SVD did not converge in 40 sweeps");
+  if (rc == -5) return fail(h, TNML_ERR_NOCONV, "Jacobi SVD did not converge in 60 sweeps");
   h->W[b].mr = m;
   h->W[b + 1].ml = m;
   h->stats.alg_flops += 4.0 * std::max(nA, nB) * (double)std::min(nA, nB) * std::min(nA, nB);

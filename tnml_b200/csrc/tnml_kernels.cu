@@ -419,14 +419,15 @@ void fat_kernel(cudaStream_t st, int mode, const double* Q, const double* F, int
 }
 
 __global__ void reduce_stats_kernel(const double* __restrict__ sp, int nblocks, double* __restrict__ stats) {
-  int i = threadIdx.x;
-  if (i >= 16) return;
+  // 16 warps, one per statistic: lanes stride over the per-block partials in a fixed order
+  const int lane = threadIdx.x & 31, i = threadIdx.x >> 5;
   double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += sp[(long)b * 16 + i];
-  stats[i] = s;
+  for (int b = lane; b < nblocks; b += 32) s += sp[(long)b * 16 + i];
+  s = warp_allsum(s);
+  if (lane == 0) stats[i] = s;
 }
 void reduce_stats(cudaStream_t st, const double* sp, int nblocks, double* stats) {
-  reduce_stats_kernel<<<1, 32, 0, st>>>(sp, nblocks, stats);
+  reduce_stats_kernel<<<1, 512, 0, st>>>(sp, nblocks, stats);
 }
 
 // ---------------------------------------------------------------------------

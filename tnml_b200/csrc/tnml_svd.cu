@@ -119,6 +119,119 @@ jacobi_offdiag_kernel(double* __restrict__ X, double* __restrict__ J, int nb, in
   if (lane == 0 && mo > 0.0) atomic_max_pos(info, mo);
 }
 
+
+// ---- shared-memory resident variants (used when 2*W columns of X and J fit) ----
+// rotate columns (already in shared memory) xi/xj (length nb) and ji/jj (length ns)
+// xi/xj point at staged columns laid out [X part (nb) | J part (ns)], ld = nb+ns.
+// The rotation is derived with two rsqrt (no divide / sqrt chain): with
+// d = b-a, h = 2g:  cos2t = |d|/r, sin2t = sign(d) h/r, r = sqrt(d^2+h^2),
+// c = sqrt((1+cos2t)/2), s = sin2t/(2c)  (|t| <= pi/4, same rotation as the
+// classical tan formula).  Returns g^2/(a b) scaled test value (0 if converged).
+__device__ __forceinline__ double rotate_pair_smem(double* __restrict__ xi, double* __restrict__ xj, int nb,
+                                                   int ld, double tol2, int lane) {
+  double a = 0.0, b = 0.0, g = 0.0;
+  for (int r = lane; r < nb; r += 32) {
+    double u = xi[r], v = xj[r];
+    a = fma(u, u, a);
+    b = fma(v, v, b);
+    g = fma(u, v, g);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    g += __shfl_xor_sync(0xffffffffu, g, o);
+  }
+  const double ab = a * b;
+  const double gg = g * g;
+  if (!(ab > 0.0) || gg <= tol2 * ab) return (ab > 0.0) ? gg / ab : 0.0;
+  const double d = b - a, h = 2.0 * g;
+  const double rinv = rsqrt(fma(d, d, h * h));
+  const double c2 = fma(0.5 * fabs(d), rinv, 0.5);   // cos^2 t
+  const double rc = rsqrt(c2);
+  const double c = c2 * rc;
+  const double s = copysign(0.5, d) * h * rinv * rc;
+  for (int r = lane; r < ld; r += 32) {
+    double u = xi[r], v = xj[r];
+    xi[r] = fma(c, u, -s * v);
+    xj[r] = fma(s, u, c * v);
+  }
+  return gg / ab;
+}
+
+// Stage columns [c0, c0+W) (slot 0..W-1) and [c1, c1+W) (slot W..2W-1) of X and J.
+template <int W>
+__device__ __forceinline__ void stage_cols(double* __restrict__ sm, double* __restrict__ X, double* __restrict__ J,
+                                           int nb, int ns, int c0, int c1, bool store, int ncols) {
+  // flat index over (slot k, row r) so that every thread has many independent
+  // global accesses in flight (the staged set is re-read from L2 every launch)
+  const int ld = nb + ns;
+  const int total = ncols * ld;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int k = i / ld, r = i - k * ld;
+    const int c = (k < W) ? (c0 + k) : (c1 + k - W);
+    if (c >= ns) continue;
+    double* gp = (r < nb) ? (X + (long)c * nb + r) : (J + (long)c * ns + (r - nb));
+    if (!store)
+      sm[i] = *gp;
+    else
+      *gp = sm[i];
+  }
+}
+
+template <int W>
+__global__ void __launch_bounds__(32 * W)
+jacobi_offdiag_smem_kernel(double* __restrict__ X, double* __restrict__ J, int nb, int ns, int nblk_e, int R,
+                           double tol2, double* __restrict__ info, const int* __restrict__ flags) {
+  if (flags[0]) return;
+  extern __shared__ __align__(16) double sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int P, Q;
+  rr_pair(nblk_e, R, blockIdx.x, P, Q);
+  if (P * W >= ns || Q * W >= ns) return;  // dummy block: nothing to do
+  const int ld = nb + ns;
+  stage_cols<W>(sm, X, J, nb, ns, P * W, Q * W, false, 2 * W);
+  __syncthreads();
+  double mo = 0.0;
+  for (int r = 0; r < W; ++r) {
+    const int ki = warp, kj = W + ((warp + r) & (W - 1));
+    if (P * W + ki < ns && Q * W + (kj - W) < ns) {
+      double* si = sm + (long)ki * ld;
+      double* sj = sm + (long)kj * ld;
+      mo = fmax(mo, rotate_pair_smem(si, sj, nb, ld, tol2, lane));
+    }
+    __syncthreads();
+  }
+  stage_cols<W>(sm, X, J, nb, ns, P * W, Q * W, true, 2 * W);
+  if (lane == 0 && mo > 0.0) atomic_max_pos(info, mo);
+}
+
+template <int W>
+__global__ void __launch_bounds__(16 * W)
+jacobi_diag_smem_kernel(double* __restrict__ X, double* __restrict__ J, int nb, int ns, double tol2,
+                        double* __restrict__ info, const int* __restrict__ flags) {
+  if (flags[0]) return;
+  extern __shared__ __align__(16) double sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * W;
+  const int ld = nb + ns;
+  stage_cols<W>(sm, X, J, nb, ns, c0, 0, false, W);
+  __syncthreads();
+  double mo = 0.0;
+  for (int r = 0; r < W - 1; ++r) {
+    int p, q;
+    rr_pair(W, r, warp, p, q);
+    if (c0 + p < ns && c0 + q < ns) {
+      double* si = sm + (long)p * ld;
+      double* sj = sm + (long)q * ld;
+      mo = fmax(mo, rotate_pair_smem(si, sj, nb, ld, tol2, lane));
+    }
+    __syncthreads();
+  }
+  stage_cols<W>(sm, X, J, nb, ns, c0, 0, true, W);
+  if (lane == 0 && mo > 0.0) atomic_max_pos(info, mo);
+}
+
 __global__ void jacobi_sweep_end_kernel(double* __restrict__ info, int* __restrict__ flags, double tol) {
   if (threadIdx.x == 0 && !flags[0]) {
     info[3] += 1.0;
@@ -297,25 +410,58 @@ int svd_split(cudaStream_t st, SvdWork& w, const double* Bc, BondGeom g, int dir
   svd_gather_kernel<<<(unsigned)((nX + 255) / 256), 256, 0, st>>>(Bc, sg, w.X);
   nl += 2;
 
-  const double tol = std::sqrt((double)nb) * 1.1102230246251565e-16;
-  const int nblk = (ns + JW - 1) / JW;
+  // |cos angle| threshold.  LAPACK dgesvj uses sqrt(nb)*eps; the rounding noise of a
+  // length-nb dot product sits right at that level and (with 28k pairs per sweep) stalls
+  // convergence, so use 8x.
+  const double tol = 8.0 * std::sqrt((double)nb) * 1.1102230246251565e-16;
+  const double tol2 = tol * tol;
+  // shared-memory resident path when 2*W staged columns (X and J parts) fit
+  const size_t need16 = (size_t)2 * 16 * (nb + ns) * sizeof(double);
+  const size_t need8 = (size_t)2 * 8 * (nb + ns) * sizeof(double);
+  int Wd = 0;
+  if (need16 <= 200 * 1024) Wd = 16;
+  else if (need8 <= 200 * 1024) Wd = 8;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(jacobi_offdiag_smem_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(jacobi_offdiag_smem_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(jacobi_diag_smem_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(jacobi_diag_smem_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  const int bw = Wd ? Wd : JW;
+  const int nblk = (ns + bw - 1) / bw;
   const int nblk_e = (nblk % 2) ? nblk + 1 : nblk;
-  const int max_sweeps = 40;
+  const double conv = Wd ? tol2 : tol;   // the smem kernels track off^2
+  const int max_sweeps = 60;
   int hflag = 0;
   int done_sweeps = 0;
   for (int sw = 0; sw < max_sweeps && !hflag; ++sw) {
-    jacobi_diag_kernel<<<nblk, 256, 0, st>>>(w.X, w.J, nb, ns, tol, w.info, w.flags);
+    if (Wd == 16) {
+      jacobi_diag_smem_kernel<16><<<nblk, 16 * 16, need16 / 2, st>>>(w.X, w.J, nb, ns, tol2, w.info, w.flags);
+    } else if (Wd == 8) {
+      jacobi_diag_smem_kernel<8><<<nblk, 16 * 8, need8 / 2, st>>>(w.X, w.J, nb, ns, tol2, w.info, w.flags);
+    } else {
+      jacobi_diag_kernel<<<nblk, 256, 0, st>>>(w.X, w.J, nb, ns, tol, w.info, w.flags);
+    }
     nl += 1;
-    if (nblk_e >= 2 && nblk > 1) {
+    if (nblk > 1) {
       for (int R = 0; R < nblk_e - 1; ++R) {
-        jacobi_offdiag_kernel<<<nblk_e / 2, 512, 0, st>>>(w.X, w.J, nb, ns, nblk_e, R, tol, w.info, w.flags);
+        if (Wd == 16)
+          jacobi_offdiag_smem_kernel<16><<<nblk_e / 2, 32 * 16, need16, st>>>(w.X, w.J, nb, ns, nblk_e, R, tol2,
+                                                                            w.info, w.flags);
+        else if (Wd == 8)
+          jacobi_offdiag_smem_kernel<8><<<nblk_e / 2, 32 * 8, need8, st>>>(w.X, w.J, nb, ns, nblk_e, R, tol2,
+                                                                          w.info, w.flags);
+        else
+          jacobi_offdiag_kernel<<<nblk_e / 2, 512, 0, st>>>(w.X, w.J, nb, ns, nblk_e, R, tol, w.info, w.flags);
         nl += 1;
       }
     }
-    jacobi_sweep_end_kernel<<<1, 32, 0, st>>>(w.info, w.flags, tol);
+    jacobi_sweep_end_kernel<<<1, 32, 0, st>>>(w.info, w.flags, conv);
     nl += 1;
     done_sweeps = sw + 1;
-    if (sw >= 3 || nblk == 1) {  // first possible convergence checks are cheap relative to a sweep
+    if (sw >= 5 || nblk == 1) {
       if (cudaMemcpyAsync(&hflag, w.flags, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
       if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
     }
