@@ -227,3 +227,41 @@ def test_shards_sum_to_whole(capi):
     assert abs(c - tot) < 1e-11 * c and nc == ncs
     for h in hs + [whole]:
         h.close()
+
+
+def test_fixedL_binary_matches_capi(capi, tmp_path):
+    """The drop-in `fixedL <inputfile>` program (host C++ over the C-ABI) reproduces,
+    log line for log line, the costs of the Python-driven path from the same W."""
+    import os
+    import re
+    import subprocess
+    from tnml_b200 import data as D
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    binp = os.path.join(root, "tnml_b200", "host", "fixedL")
+    if not os.path.exists(binp):
+        pytest.skip("host binary not built")
+    side = 6
+    pix, labels = D.synthetic_digits(200, side, seed=11)
+    u8 = (pix * 255).round().astype(np.uint8)
+    # per-label cap 20 keeps all 200 images (20 per label), file order
+    D.write_idx_files(str(tmp_path / "d"), u8, labels, side)
+    W = D.random_mps(side * side, 2, 4, seed=4)
+    D.write_sites_file(str(tmp_path / "sites"), side * side)
+    D.write_mps_file(str(tmp_path / "W"), W)
+    (tmp_path / "in").write_text(
+        f"input\n{{\ndatadir = {tmp_path}/d\nNtrain = 20\nimglen = {side}\nNbatch = 4\nmaxm = 6\nminm = 3\n"
+        f"cutoff = 1E-10\nNsweep = 1\nNpass = 3\nnthread = 2\n}}\n")
+    r = subprocess.run([binp, "in"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    costs = [float(x) for x in re.findall(r"--> After SVD, Cost = ([0-9.eE+-]+)", r.stdout)]
+    ms = [int(x) for x in re.findall(r"Original m=\d+, New m=(\d+)", r.stdout)]
+    assert len(costs) == 2 * (side * side - 1)
+    feat = D.phi(u8.astype(np.float64) / 255.0)
+    h = _gpu_state(capi, feat, labels.astype(np.int64), W)
+    p = capi.BondParams(3, 0.0, 1e-10, 1e-10, 6, 3, 0)
+    for k, (b, ha) in enumerate(O.sweep_schedule(side * side)):
+        res = h.bond_update(b, ha, p)
+        assert res.newm == ms[k]
+        assert abs(res.cost / 200 - costs[k]) < 2e-10 + 1e-9 * costs[k], k    # printed with 10 decimals
+    assert "Before starting DMRG Cost" in r.stdout and "Writing W to disk" in r.stdout
+    h.close()

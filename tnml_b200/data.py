@@ -7,6 +7,7 @@ from __future__ import annotations
 import os
 import re
 import struct
+import struct
 
 import numpy as np
 
@@ -164,3 +165,43 @@ def random_mps(N, d=2, m=10, seed=1, noise=0.3, jc=None):
     W[1] = W[1] / np.linalg.norm(W[1])
     W[jc] = W[jc] / np.linalg.norm(W[jc])
     return W
+
+
+# ---- files shared with the C++ host program (tnml_b200/host/itensor_lite.h) -----
+def _w_index(f, idx_id, m, name, typ):
+    nb, tb = name.encode(), typ.encode()
+    f.write(struct.pack("<qqq", idx_id, m, len(nb)) + nb + struct.pack("<q", len(tb)) + tb)
+
+
+def write_sites_file(path, N, d=2):
+    """`sites` file in the TNMLS1 format read by fixedL (SiteSet::read)."""
+    with open(path, "wb") as f:
+        f.write(b"TNMLS1\0\0" + struct.pack("<q", N))
+        for j in range(1, N + 1):
+            _w_index(f, j, d, f"S{j}", "Site")
+
+
+def write_mps_file(path, W, d=2):
+    """`W` file in the TNMLW1 format (index order left, site, right [, L])."""
+    N = len(W) - 1
+    with open(path, "wb") as f:
+        f.write(b"TNMLW1\0\0" + struct.pack("<q", N))
+        for j in range(1, N + 1):
+            A = np.ascontiguousarray(W[j], np.float64)
+            f.write(struct.pack("<q", A.ndim))
+            _w_index(f, 1000 + j - 1, A.shape[0], f"l{j - 1}", "Link")
+            _w_index(f, j, d, f"S{j}", "Site")
+            _w_index(f, 1000 + j, A.shape[2], f"l{j}", "Link")
+            if A.ndim == 4:
+                _w_index(f, 5000, NL, "L", "Label")
+            f.write(struct.pack("<q", A.size) + A.tobytes())
+
+
+def write_idx_files(datadir, pix_u8, labels, side, kind="train"):
+    """MNIST-format idx3/idx1 files (for running the fixedL binary on synthetic data)."""
+    os.makedirs(datadir, exist_ok=True)
+    n = pix_u8.shape[0]
+    with open(os.path.join(datadir, f"{kind}-images-idx3-ubyte"), "wb") as f:
+        f.write(struct.pack(">IIII", 2051, n, side, side) + np.ascontiguousarray(pix_u8, np.uint8).tobytes())
+    with open(os.path.join(datadir, f"{kind}-labels-idx1-ubyte"), "wb") as f:
+        f.write(struct.pack(">II", 2049, n) + np.ascontiguousarray(labels, np.uint8).tobytes())
