@@ -265,3 +265,36 @@ def test_fixedL_binary_matches_capi(capi, tmp_path):
         assert abs(res.cost / 200 - costs[k]) < 2e-10 + 1e-9 * costs[k], k    # printed with 10 decimals
     assert "Before starting DMRG Cost" in r.stdout and "Writing W to disk" in r.stdout
     h.close()
+
+
+@pytest.mark.parametrize("b,ha", [(6, 1), (7, 1), (8, 1), (8, 2), (7, 2), (10, 2)])
+def test_svd_qr_preconditioned_path(capi, b, ha):
+    """Larger bond matrices (>= 32 columns) go through Householder QR + Jacobi on R^T
+    + apply-Q; rank-deficient + noise spectra like a freshly optimised bond tensor."""
+    feat, labels, W = make_problem(N=16, NT=64, m0=20)
+    ts = O.TrainStates(feat, labels)
+    ts.init(W)
+    h = _gpu_state(capi, feat, labels, W)
+    _walk_both(h, ts, W, capi, b)
+    rng = np.random.default_rng(b * 10 + ha)
+    B0 = O.form_bond(W[b], W[b + 1])
+    for noise in (1e-1, 1e-6):
+        B = B0 + noise * np.linalg.norm(B0) / np.sqrt(B0.size) * rng.standard_normal(B0.shape)
+        for (maxm, minm, cutoff) in [(1000, 1, 0.0), (20, 10, 1e-10)]:
+            Wb, Wb1, m, te = O.svd_split(B, b, ha, 8, maxm, minm, cutoff)
+            h.bond_load(B)
+            gm, gte = h.svd_split(capi.FROMLEFT if ha == 1 else capi.FROMRIGHT, cutoff, maxm, minm)
+            assert gm == m
+            assert abs(gte - te) <= 1e-8 * max(te, 1e-300) + 1e-22 * np.linalg.norm(B) ** 2
+            gWb, gWb1 = h.get_site(b), h.get_site(b + 1)
+            assert rel(O.form_bond(gWb, gWb1), O.form_bond(Wb, Wb1)) < 1e-10
+            iso = gWb if ha == 1 else gWb1
+            if ha == 1:
+                U = (np.transpose(iso, (0, 1, 3, 2)) if iso.ndim == 4 else iso).reshape(-1, m)
+                assert rel(U.T @ U, np.eye(m)) < 1e-12
+            else:
+                V = iso.reshape(m, -1)
+                assert rel(V @ V.T, np.eye(m)) < 1e-12
+            h.set_site(b, W[b])
+            h.set_site(b + 1, W[b + 1])
+    h.close()

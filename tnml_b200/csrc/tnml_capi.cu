@@ -544,7 +544,8 @@ int tnml_destroy(tnml_handle h) {
   for (DBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   void* ptrs[] = {h->feat, h->labels, h->ones, h->P, h->pred, h->stats_partial, h->dscal, h->dot_scratch,
-                  h->svd.X, h->svd.J, h->svd.sig2, h->svd.perm, h->svd.info, h->svd.flags};
+                  h->svd.X, h->svd.J, h->svd.sig2, h->svd.perm, h->svd.info, h->svd.flags,
+                  h->svd.M, h->svd.tau, h->svd.ready, h->svd.Y};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->hpin) cudaFreeHost(h->hpin);

@@ -78,6 +78,13 @@ struct SvdWork {
   int* flags = nullptr;    // [4]: 0 converged
   long capX = 0, capJ = 0;
   int capS = 0;
+  // QR-preconditioned path
+  double* M = nullptr;     // [ns][ns] R^T, then its rotated columns
+  double* tau = nullptr;   // [ns]
+  int* ready = nullptr;    // [ns] dataflow flags
+  double* Y = nullptr;     // [kept][nb] big-side unit vectors
+  long capM = 0, capY = 0;
+  int use_qr = -1;         // -1 auto, 0 never, 1 always (TNML_SVD_QR)
 };
 // Gather canonical B into X (tall orientation), run block one-sided Jacobi,
 // sort, apply ITensor's truncation rule, scatter U -> W(c), S*V -> W(c+dc).

@@ -16,6 +16,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 namespace tnml {
 
@@ -159,6 +160,70 @@ __device__ __forceinline__ double rotate_pair_smem(double* __restrict__ xi, doub
   return gg / ab;
 }
 
+// Fully unrolled variant for rows, ns <= 32*R: the two A columns stay in registers between
+// the dot products and the update, every shared-memory access of a phase is issued
+// back to back (the loop version above is latency bound: ~26 cycles per instruction).
+template <int R>
+__device__ __forceinline__ double rotate_pair_regs(double* __restrict__ xi, double* __restrict__ xj, int nb,
+                                                   int ns, double tol2, int lane) {
+  double u[R], v[R];
+  double a = 0.0, b = 0.0, g = 0.0;
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const int r = lane + 32 * i;
+    u[i] = (r < nb) ? xi[r] : 0.0;
+    v[i] = (r < nb) ? xj[r] : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    a = fma(u[i], u[i], a);
+    b = fma(v[i], v[i], b);
+    g = fma(u[i], v[i], g);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    g += __shfl_xor_sync(0xffffffffu, g, o);
+  }
+  const double ab = a * b;
+  const double gg = g * g;
+  if (!(ab > 0.0)) return 0.0;
+  if (gg <= tol2 * ab) return tol2 * 0.5;   // converged pair: report "below threshold"
+  const double d = b - a, h = 2.0 * g;
+  const double rinv = rsqrt(fma(d, d, h * h));
+  const double c2 = fma(0.5 * fabs(d), rinv, 0.5);
+  const double rc = rsqrt(c2);
+  const double c = c2 * rc;
+  const double s = copysign(0.5, d) * h * rinv * rc;
+  double* ji = xi + nb;
+  double* jj = xj + nb;
+  double p[R], q[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const int r = lane + 32 * i;
+    p[i] = (r < ns) ? ji[r] : 0.0;
+    q[i] = (r < ns) ? jj[r] : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const int r = lane + 32 * i;
+    if (r < nb) {
+      xi[r] = fma(c, u[i], -s * v[i]);
+      xj[r] = fma(s, u[i], c * v[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const int r = lane + 32 * i;
+    if (r < ns) {
+      ji[r] = fma(c, p[i], -s * q[i]);
+      jj[r] = fma(s, p[i], c * q[i]);
+    }
+  }
+  return gg / ab;
+}
+
 // Stage columns [c0, c0+W) (slot 0..W-1) and [c1, c1+W) (slot W..2W-1) of X and J.
 template <int W>
 __device__ __forceinline__ void stage_cols(double* __restrict__ sm, double* __restrict__ X, double* __restrict__ J,
@@ -166,6 +231,25 @@ __device__ __forceinline__ void stage_cols(double* __restrict__ sm, double* __re
   // flat index over (slot k, row r) so that every thread has many independent
   // global accesses in flight (the staged set is re-read from L2 every launch)
   const int ld = nb + ns;
+  if (((nb | ns) & 1) == 0) {   // 16-byte path: every column start is 16-byte aligned
+    const int ld2 = ld >> 1, nb2 = nb >> 1, ns2 = ns >> 1;
+    const int total = ncols * ld2;
+    double2* sm2 = reinterpret_cast<double2*>(sm);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int k = i / ld2, r = i - k * ld2;
+      const int c = (k < W) ? (c0 + k) : (c1 + k - W);
+      if (c >= ns) continue;
+      double2* gp = (r < nb2) ? (reinterpret_cast<double2*>(X + (long)c * nb) + r)
+                              : (reinterpret_cast<double2*>(J + (long)c * ns) + (r - nb2));
+      if (!store)
+        sm2[i] = __ldcg(gp);
+      else
+        __stcg(gp, sm2[i]);
+    }
+    (void)ns2;
+    return;
+  }
   const int total = ncols * ld;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int k = i / ld, r = i - k * ld;
@@ -198,7 +282,8 @@ jacobi_offdiag_smem_kernel(double* __restrict__ X, double* __restrict__ J, int n
     if (P * W + ki < ns && Q * W + (kj - W) < ns) {
       double* si = sm + (long)ki * ld;
       double* sj = sm + (long)kj * ld;
-      mo = fmax(mo, rotate_pair_smem(si, sj, nb, ld, tol2, lane));
+      mo = fmax(mo, (nb <= 256 && ns <= 256) ? rotate_pair_regs<8>(si, sj, nb, ns, tol2, lane)
+                                             : rotate_pair_smem(si, sj, nb, ld, tol2, lane));
     }
     __syncthreads();
   }
@@ -224,7 +309,8 @@ jacobi_diag_smem_kernel(double* __restrict__ X, double* __restrict__ J, int nb, 
     if (c0 + p < ns && c0 + q < ns) {
       double* si = sm + (long)p * ld;
       double* sj = sm + (long)q * ld;
-      mo = fmax(mo, rotate_pair_smem(si, sj, nb, ld, tol2, lane));
+      mo = fmax(mo, (nb <= 256 && ns <= 256) ? rotate_pair_regs<8>(si, sj, nb, ns, tol2, lane)
+                                             : rotate_pair_smem(si, sj, nb, ld, tol2, lane));
     }
     __syncthreads();
   }
@@ -361,6 +447,183 @@ __global__ void svd_scatter_kernel(const double* __restrict__ X, const double* _
     Wb1[e] = v;
 }
 
+
+// ---------------------------------------------------------------------------
+// QR preconditioning (Drmac-Veselic): X = Q R by Householder, then one-sided
+// Jacobi on R^T.  On graded / nearly rank-deficient bond matrices plain Jacobi
+// needs 25-40 sweeps, Jacobi on R^T about 10 (measured, DESIGN.md "SVD").
+//
+// Dataflow Householder QR: one warp owns one column (kept in registers); it
+// applies reflector k as soon as column k has published it (flag in global
+// memory), then forms its own reflector.  No grid-wide barrier.  All ns warps
+// must be co-resident (ns/8 CTAs <= number of SMs).
+template <int RPL>   // rows per lane: nb <= 32*RPL
+__global__ void __launch_bounds__(256)
+qr_dataflow_kernel(double* __restrict__ X, int nb, int ns, double* __restrict__ tau, volatile int* ready) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= ns) return;
+  double* aj = X + (long)j * nb;
+  double a[RPL];
+#pragma unroll
+  for (int i = 0; i < RPL; ++i) {
+    int r = lane + 32 * i;
+    a[i] = (r < nb) ? aj[r] : 0.0;
+  }
+  for (int k = 0; k < j; ++k) {
+    if (lane == 0)
+      while (ready[k] == 0) {
+      }
+    __syncwarp();
+    __threadfence();
+    const double* vk = X + (long)k * nb;
+    const double tk = __ldcg(tau + k);
+    double dot = 0.0;
+    if (RPL <= 20) {
+      double v[RPL <= 20 ? RPL : 1];
+#pragma unroll
+      for (int i = 0; i < (RPL <= 20 ? RPL : 1); ++i) {
+        int r = lane + 32 * i;
+        v[i] = (r > k && r < nb) ? __ldcg(vk + r) : ((r == k) ? 1.0 : 0.0);
+        dot = fma(v[i], a[i], dot);
+      }
+      dot = wsum(dot);
+      const double f = tk * dot;
+#pragma unroll
+      for (int i = 0; i < (RPL <= 20 ? RPL : 1); ++i) a[i] = fma(-f, v[i], a[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) {
+        int r = lane + 32 * i;
+        double vv = (r > k && r < nb) ? __ldcg(vk + r) : ((r == k) ? 1.0 : 0.0);
+        dot = fma(vv, a[i], dot);
+      }
+      dot = wsum(dot);
+      const double f = tk * dot;
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) {
+        int r = lane + 32 * i;
+        double vv = (r > k && r < nb) ? __ldcg(vk + r) : ((r == k) ? 1.0 : 0.0);
+        a[i] = fma(-f, vv, a[i]);
+      }
+    }
+  }
+  // own reflector (LAPACK dlarfg): H = I - tau v v^T, v(j) = 1
+  double alpha = 0.0, xn2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < RPL; ++i) {
+    int r = lane + 32 * i;
+    if (r == j) alpha = a[i];
+    if (r > j && r < nb) xn2 = fma(a[i], a[i], xn2);
+  }
+  alpha = wsum(alpha);
+  xn2 = wsum(xn2);
+  double tj = 0.0, beta = alpha, scale = 0.0;
+  if (xn2 > 0.0) {
+    beta = -copysign(sqrt(fma(alpha, alpha, xn2)), alpha);
+    tj = (beta - alpha) / beta;
+    scale = 1.0 / (alpha - beta);
+  }
+#pragma unroll
+  for (int i = 0; i < RPL; ++i) {
+    int r = lane + 32 * i;
+    if (r < nb) {
+      double out = a[i];
+      if (r == j) out = beta;
+      if (r > j) out = a[i] * scale;
+      __stcg(aj + r, out);
+    }
+  }
+  if (lane == 0) __stcg(tau + j, tj);
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) ready[j] = 1;
+}
+
+// M = R^T as a column-major ns x ns matrix: M[:, j] = row j of R (upper triangular)
+__global__ void rt_form_kernel(const double* __restrict__ X, int nb, int ns, double* __restrict__ M) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)ns * ns) return;
+  int c = (int)(idx % ns);   // row index inside column j of M
+  int j = (int)(idx / ns);
+  M[idx] = (c >= j) ? X[(long)c * nb + j] : 0.0;
+}
+
+// big-side unit vectors: Y[i] = Q * [J'[:, perm[i]]; 0].  One warp per kept vector.
+template <int RPL>
+__global__ void __launch_bounds__(256)
+apply_q_kernel(const double* __restrict__ X, const double* __restrict__ tau, const double* __restrict__ Jm,
+               const int* __restrict__ perm, int nb, int ns, int m, double* __restrict__ Y) {
+  const int lane = threadIdx.x & 31;
+  const int i0 = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i0 >= m) return;
+  const double* jc = Jm + (long)perm[i0] * ns;
+  double y[RPL];
+#pragma unroll
+  for (int i = 0; i < RPL; ++i) {
+    int r = lane + 32 * i;
+    y[i] = (r < ns) ? jc[r] : 0.0;
+  }
+  for (int k = ns - 1; k >= 0; --k) {
+    const double* vk = X + (long)k * nb;
+    const double tk = tau[k];
+    double dot = 0.0;
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+      int r = lane + 32 * i;
+      double vv = (r > k && r < nb) ? vk[r] : ((r == k) ? 1.0 : 0.0);
+      dot = fma(vv, y[i], dot);
+    }
+    dot = wsum(dot);
+    const double f = tk * dot;
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+      int r = lane + 32 * i;
+      double vv = (r > k && r < nb) ? vk[r] : ((r == k) ? 1.0 : 0.0);   // L1 hit
+      y[i] = fma(-f, vv, y[i]);
+    }
+  }
+  double* out = Y + (long)i0 * nb;
+#pragma unroll
+  for (int i = 0; i < RPL; ++i) {
+    int r = lane + 32 * i;
+    if (r < nb) out[r] = y[i];
+  }
+}
+
+// QR path scatter: big side = unit vectors Y[k][nb]; small side = columns of M (sigma-scaled)
+__global__ void svd_scatter_qr_kernel(const double* __restrict__ Y, const double* __restrict__ M,
+                                      const double* __restrict__ sig2, const int* __restrict__ perm, SvdGeom sg,
+                                      int isoIsA, int m, double* __restrict__ Wb, double* __restrict__ Wb1) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long nAm = (long)sg.nA * m, nBm = (long)sg.nB * m;
+  if (idx >= nAm + nBm) return;
+  const bool sideA = idx < nAm;
+  long e = sideA ? idx : idx - nAm;
+  int k, i;
+  if (sideA) {
+    int l = (int)(e % sg.nlA);
+    long r = e / sg.nlA;
+    k = (int)(r % m);
+    int as = (int)(r / m);
+    i = as * sg.nlA + l;
+  } else {
+    k = (int)(e / sg.nB);
+    i = (int)(e % sg.nB);
+  }
+  const int c = perm[k];
+  const bool thisIsBig = (sideA == (sg.bigIsA != 0));
+  const bool thisIsIso = (sideA == (isoIsA != 0));
+  double v = thisIsBig ? Y[(long)k * sg.nb + i] : M[(long)c * sg.ns + i];
+  const double sg1 = sqrt(sig2[c]);
+  if (thisIsBig && !thisIsIso) v *= sg1;                       // unit -> sigma * unit
+  if (!thisIsBig && thisIsIso) v = (sg1 > 0.0) ? v / sg1 : 0.0;  // sigma * unit -> unit
+  if (sideA)
+    Wb[e] = v;
+  else
+    Wb1[e] = v;
+}
+
 static int ensure(SvdWork& w, long nX, int ns) {
   if (nX > w.capX) {
     if (w.X) cudaFree(w.X);
@@ -384,40 +647,34 @@ static int ensure(SvdWork& w, long nX, int ns) {
     if (cudaMalloc(&w.info, 8 * sizeof(double)) != cudaSuccess) return -1;
     if (cudaMalloc(&w.flags, 4 * sizeof(int)) != cudaSuccess) return -1;
   }
+  if (nJ > w.capM) {   // QR path: R^T, tau, ready flags
+    if (w.M) cudaFree(w.M);
+    if (w.tau) cudaFree(w.tau);
+    if (w.ready) cudaFree(w.ready);
+    if (cudaMalloc(&w.M, nJ * sizeof(double)) != cudaSuccess) return -1;
+    if (cudaMalloc(&w.tau, ns * sizeof(double)) != cudaSuccess) return -1;
+    if (cudaMalloc(&w.ready, ns * sizeof(int)) != cudaSuccess) return -1;
+    w.capM = nJ;
+  }
+  if (nX > w.capY) {
+    if (w.Y) cudaFree(w.Y);
+    if (cudaMalloc(&w.Y, nX * sizeof(double)) != cudaSuccess) return -1;
+    w.capY = nX;
+  }
   return 0;
 }
 
-int svd_split(cudaStream_t st, SvdWork& w, const double* Bc, BondGeom g, int dir, double cutoff, int maxm,
-              int minm, int do_rel_cutoff, double* Wb_out, double* Wb1_out, int* newm, double* truncerr,
-              int* sweeps, long* launches) {
-  SvdGeom sg;
-  sg.g = g;
-  sg.nlA = g.lab_b ? NL : 1;
-  sg.nlB = g.lab_b1 ? NL : 1;
-  sg.nA = 2 * g.ml * sg.nlA;
-  sg.nB = 2 * g.mr * sg.nlB;
-  sg.bigIsA = (sg.nA >= sg.nB) ? 1 : 0;
-  sg.nb = sg.bigIsA ? sg.nA : sg.nB;
-  sg.ns = sg.bigIsA ? sg.nB : sg.nA;
-  const int ns = sg.ns, nb = sg.nb;
-  if (ensure(w, (long)nb * ns, ns) != 0) return -2;
-  long nl = 0;
-
-  long nJ = (long)ns * ns;
-  long ninit = nJ > 8 ? nJ : 8;
-  svd_init_kernel<<<(unsigned)((ninit + 255) / 256), 256, 0, st>>>(w.J, ns, w.info, w.flags);
-  long nX = (long)nb * ns;
-  svd_gather_kernel<<<(unsigned)((nX + 255) / 256), 256, 0, st>>>(Bc, sg, w.X);
-  nl += 2;
-
-  // |cos angle| threshold.  LAPACK dgesvj uses sqrt(nb)*eps; the rounding noise of a
-  // length-nb dot product sits right at that level and (with 28k pairs per sweep) stalls
+// Block one-sided Jacobi on the column-major matrix A (rows x ns), rotations accumulated
+// in Jm (ns x ns, must hold the starting orthogonal matrix).  Returns 0 when converged.
+static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, int rows, int ns, long& nl) {
+  // |cos angle| threshold.  LAPACK dgesvj uses sqrt(rows)*eps; the rounding noise of a
+  // dot product sits right at that level and (with 28k pairs per sweep) stalls
   // convergence, so use 8x.
-  const double tol = 8.0 * std::sqrt((double)nb) * 1.1102230246251565e-16;
+  const double tol = 8.0 * std::sqrt((double)rows) * 1.1102230246251565e-16;
   const double tol2 = tol * tol;
-  // shared-memory resident path when 2*W staged columns (X and J parts) fit
-  const size_t need16 = (size_t)2 * 16 * (nb + ns) * sizeof(double);
-  const size_t need8 = (size_t)2 * 8 * (nb + ns) * sizeof(double);
+  // shared-memory resident path when 2*W staged columns (A and J parts) fit
+  const size_t need16 = (size_t)2 * 16 * (rows + ns) * sizeof(double);
+  const size_t need8 = (size_t)2 * 8 * (rows + ns) * sizeof(double);
   int Wd = 0;
   if (need16 <= 200 * 1024) Wd = 16;
   else if (need8 <= 200 * 1024) Wd = 8;
@@ -435,38 +692,94 @@ int svd_split(cudaStream_t st, SvdWork& w, const double* Bc, BondGeom g, int dir
   const double conv = Wd ? tol2 : tol;   // the smem kernels track off^2
   const int max_sweeps = 60;
   int hflag = 0;
-  int done_sweeps = 0;
   for (int sw = 0; sw < max_sweeps && !hflag; ++sw) {
     if (Wd == 16) {
-      jacobi_diag_smem_kernel<16><<<nblk, 16 * 16, need16 / 2, st>>>(w.X, w.J, nb, ns, tol2, w.info, w.flags);
+      jacobi_diag_smem_kernel<16><<<nblk, 16 * 16, need16 / 2, st>>>(A, Jm, rows, ns, tol2, w.info, w.flags);
     } else if (Wd == 8) {
-      jacobi_diag_smem_kernel<8><<<nblk, 16 * 8, need8 / 2, st>>>(w.X, w.J, nb, ns, tol2, w.info, w.flags);
+      jacobi_diag_smem_kernel<8><<<nblk, 16 * 8, need8 / 2, st>>>(A, Jm, rows, ns, tol2, w.info, w.flags);
     } else {
-      jacobi_diag_kernel<<<nblk, 256, 0, st>>>(w.X, w.J, nb, ns, tol, w.info, w.flags);
+      jacobi_diag_kernel<<<nblk, 256, 0, st>>>(A, Jm, rows, ns, tol, w.info, w.flags);
     }
     nl += 1;
     if (nblk > 1) {
       for (int R = 0; R < nblk_e - 1; ++R) {
         if (Wd == 16)
-          jacobi_offdiag_smem_kernel<16><<<nblk_e / 2, 32 * 16, need16, st>>>(w.X, w.J, nb, ns, nblk_e, R, tol2,
-                                                                            w.info, w.flags);
+          jacobi_offdiag_smem_kernel<16><<<nblk_e / 2, 32 * 16, need16, st>>>(A, Jm, rows, ns, nblk_e, R, tol2, w.info,
+                                                                            w.flags);
         else if (Wd == 8)
-          jacobi_offdiag_smem_kernel<8><<<nblk_e / 2, 32 * 8, need8, st>>>(w.X, w.J, nb, ns, nblk_e, R, tol2,
-                                                                          w.info, w.flags);
+          jacobi_offdiag_smem_kernel<8><<<nblk_e / 2, 32 * 8, need8, st>>>(A, Jm, rows, ns, nblk_e, R, tol2, w.info,
+                                                                          w.flags);
         else
-          jacobi_offdiag_kernel<<<nblk_e / 2, 512, 0, st>>>(w.X, w.J, nb, ns, nblk_e, R, tol, w.info, w.flags);
+          jacobi_offdiag_kernel<<<nblk_e / 2, 512, 0, st>>>(A, Jm, rows, ns, nblk_e, R, tol, w.info, w.flags);
         nl += 1;
       }
     }
     jacobi_sweep_end_kernel<<<1, 32, 0, st>>>(w.info, w.flags, conv);
     nl += 1;
-    done_sweeps = sw + 1;
-    if (sw >= 5 || nblk == 1) {
+    if (sw >= 3 || nblk == 1) {
       if (cudaMemcpyAsync(&hflag, w.flags, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
       if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
     }
   }
-  svd_finalize_kernel<<<1, 1024, 0, st>>>(w.X, nb, ns, w.sig2, w.perm, cutoff, maxm, minm, do_rel_cutoff, w.info);
+  return hflag ? 0 : -5;
+}
+
+template <int RPL>
+static void launch_qr(cudaStream_t st, SvdWork& w, int nb, int ns) {
+  qr_dataflow_kernel<RPL><<<(ns + 7) / 8, 256, 0, st>>>(w.X, nb, ns, w.tau, w.ready);
+}
+template <int RPL>
+static void launch_apply_q(cudaStream_t st, SvdWork& w, int nb, int ns, int m) {
+  apply_q_kernel<RPL><<<(m + 7) / 8, 256, 0, st>>>(w.X, w.tau, w.J, w.perm, nb, ns, m, w.Y);
+}
+
+int svd_split(cudaStream_t st, SvdWork& w, const double* Bc, BondGeom g, int dir, double cutoff, int maxm,
+              int minm, int do_rel_cutoff, double* Wb_out, double* Wb1_out, int* newm, double* truncerr,
+              int* sweeps, long* launches) {
+  SvdGeom sg;
+  sg.g = g;
+  sg.nlA = g.lab_b ? NL : 1;
+  sg.nlB = g.lab_b1 ? NL : 1;
+  sg.nA = 2 * g.ml * sg.nlA;
+  sg.nB = 2 * g.mr * sg.nlB;
+  sg.bigIsA = (sg.nA >= sg.nB) ? 1 : 0;
+  sg.nb = sg.bigIsA ? sg.nA : sg.nB;
+  sg.ns = sg.bigIsA ? sg.nB : sg.nA;
+  const int ns = sg.ns, nb = sg.nb;
+  if (ensure(w, (long)nb * ns, ns) != 0) return -2;
+  long nl = 0;
+  if (w.use_qr < 0) {
+    const char* e = getenv("TNML_SVD_QR");
+    w.use_qr = e ? atoi(e) : 2;   // 2 = auto
+  }
+  // QR preconditioning pays off from a few dozen columns on; it needs one resident warp per
+  // column and the column in registers (nb <= 32*96)
+  const bool qr = (w.use_qr == 1 || (w.use_qr == 2 && ns >= 32)) && nb <= 32 * 96 && ns <= 8 * 140;
+
+  long nJ = (long)ns * ns;
+  long ninit = nJ > 8 ? nJ : 8;
+  svd_init_kernel<<<(unsigned)((ninit + 255) / 256), 256, 0, st>>>(w.J, ns, w.info, w.flags);
+  long nX = (long)nb * ns;
+  svd_gather_kernel<<<(unsigned)((nX + 255) / 256), 256, 0, st>>>(Bc, sg, w.X);
+  nl += 2;
+
+  int rc;
+  if (qr) {
+    if (cudaMemsetAsync(w.ready, 0, ns * sizeof(int), st) != cudaSuccess) return -2;
+    if (nb <= 32 * 8) launch_qr<8>(st, w, nb, ns);
+    else if (nb <= 32 * 20) launch_qr<20>(st, w, nb, ns);
+    else if (nb <= 32 * 40) launch_qr<40>(st, w, nb, ns);
+    else launch_qr<96>(st, w, nb, ns);
+    rt_form_kernel<<<(unsigned)((nJ + 255) / 256), 256, 0, st>>>(w.X, nb, ns, w.M);
+    nl += 3;
+    rc = jacobi_iterate(st, w, w.M, w.J, ns, ns, nl);
+    if (rc == -2) return rc;
+    svd_finalize_kernel<<<1, 1024, 0, st>>>(w.M, ns, ns, w.sig2, w.perm, cutoff, maxm, minm, do_rel_cutoff, w.info);
+  } else {
+    rc = jacobi_iterate(st, w, w.X, w.J, nb, ns, nl);
+    if (rc == -2) return rc;
+    svd_finalize_kernel<<<1, 1024, 0, st>>>(w.X, nb, ns, w.sig2, w.perm, cutoff, maxm, minm, do_rel_cutoff, w.info);
+  }
   nl += 1;
   double hinfo[8];
   if (cudaMemcpyAsync(hinfo, w.info, sizeof(hinfo), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
@@ -475,15 +788,24 @@ int svd_split(cudaStream_t st, SvdWork& w, const double* Bc, BondGeom g, int dir
   *newm = m;
   *truncerr = hinfo[2];
   *sweeps = (int)hinfo[3];
-  (void)done_sweeps;
   const int isoIsA = (dir == 1) ? 1 : 0;
   long nout = (long)(sg.nA + sg.nB) * m;
-  svd_scatter_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(w.X, w.J, w.sig2, w.perm, sg, isoIsA, m,
-                                                                    Wb_out, Wb1_out);
-  nl += 1;
+  if (qr) {
+    if (nb <= 32 * 8) launch_apply_q<8>(st, w, nb, ns, m);
+    else if (nb <= 32 * 20) launch_apply_q<20>(st, w, nb, ns, m);
+    else if (nb <= 32 * 40) launch_apply_q<40>(st, w, nb, ns, m);
+    else launch_apply_q<96>(st, w, nb, ns, m);
+    svd_scatter_qr_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(w.Y, w.M, w.sig2, w.perm, sg, isoIsA, m,
+                                                                       Wb_out, Wb1_out);
+    nl += 2;
+  } else {
+    svd_scatter_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(w.X, w.J, w.sig2, w.perm, sg, isoIsA, m,
+                                                                      Wb_out, Wb1_out);
+    nl += 1;
+  }
   if (launches) *launches += nl;
   if (cudaGetLastError() != cudaSuccess) return -2;
-  return hflag ? 0 : -5;
+  return rc;
 }
 
 }  // namespace tnml

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tnml_b200 import capi, data  # noqa: E402
 
 
-def main(m=120):
+def main(m=120, only=None):
     N, NT = 20, 64
     pix, labels = data.synthetic_digits(NT, 14, seed=1)
     feat = data.phi(pix[:, 80:80 + N])
@@ -39,6 +39,8 @@ def main(m=120):
         V = rng.standard_normal((min(rows, cols), cols))
         cases["graded 1e-9"] = ((U * np.logspace(0, -9, U.shape[1])) @ V).reshape(shape)
         for name, B in cases.items():
+            if only and only not in name:
+                continue
             for rep in range(2):
                 h.bond_load(B)
                 h.set_timing(True)
@@ -69,4 +71,4 @@ def main(m=120):
 
 
 if __name__ == "__main__":
-    main(int(sys.argv[1]) if len(sys.argv) > 1 else 120)
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 120, sys.argv[2] if len(sys.argv) > 2 else None)
