@@ -303,7 +303,7 @@ int forward(tnml_handle h, const double* X, int mode, double* dstats) {
     if (mode == FAT_GRAD) TRY(ensure(h, h->Z, (size_t)NT * mf));
     {
       PhaseTimer t(h, PH_PROJ);
-      krgemm(h->st, 2, thin.p, mt, mt, fth, 1, X, X + mf, 2L * mf, mf, ffa, h->Q.p, mf, NT);
+      krgemm(h->st, 4, thin.p, mt, mt, fth, ffa, 1, X, mf, mf, h->Q.p, mf, NT, h->num_sm);
       CKL();
     }
     {
@@ -323,7 +323,7 @@ int forward(tnml_handle h, const double* X, int mode, double* dstats) {
     if (mode == FAT_GRAD) TRY(ensure(h, h->Z, (size_t)NT * J));
     {
       PhaseTimer t(h, PH_PROJ);
-      krgemm(h->st, 2, le.p, g.ml, g.ml, featp(h, b), 1, X, X + J, 2 * J, (int)J, featp(h, b + 1), h->Q.p, J, NT);
+      krgemm(h->st, 4, le.p, g.ml, g.ml, featp(h, b), featp(h, b + 1), 1, X, J, (int)J, h->Q.p, J, NT, h->num_sm);
       CKL();
     }
     {
@@ -362,10 +362,10 @@ int backward(tnml_handle h) {
   } else {
     thin = le.p, mt = le.m, f1 = featp(h, b), f2 = featp(h, b + 1), J = (long)NL * g.mr;
   }
-  const int ns = krgram_splits(mt, (int)J, 2, NT, h->num_sm);
+  const int ns = krgram_splits(mt, 4, (int)J, NT, h->num_sm);
   TRY(ensure(h, h->Gpart, (size_t)ns * n));
   PhaseTimer t(h, PH_GRAD);
-  krgram(h->st, 2, thin, mt, mt, f1, f2, h->Z.p, J, (int)J, h->Gpart.p, NT, ns);
+  krgram(h->st, 4, thin, mt, mt, f1, f2, h->Z.p, J, (int)J, h->Gpart.p, NT, ns);
   CKL();
   reduce_partials(h->st, h->Gpart.p, ns, n, h->G.p);
   CKL();
@@ -456,7 +456,7 @@ int advance_env(tnml_handle h, int c, int right) {
   const long rows = pe.fat ? NT * NL : NT;
   const int div = pe.fat ? NL : 1;
   const int J = kout * (w.lab ? NL : 1);
-  krgemm(h->st, 1, pe.p, kin, kin, featp(h, c), div, Bm, nullptr, J, J, nullptr, ns.p, J, rows);
+  krgemm(h->st, 2, pe.p, kin, kin, featp(h, c), nullptr, div, Bm, J, J, ns.p, J, rows, h->num_sm);
   CKL();
   h->stats.launches += 1;
   h->stats.alg_flops += (double)rows * 4.0 * kin * J;

@@ -17,182 +17,202 @@ constexpr int BN = 64;
 constexpr int BK = 16;
 constexpr int NTHR = 256;
 
-template <int NB>
-__device__ __forceinline__ void tile_fma(const double* __restrict__ A, const double* __restrict__ B,
-                                         double (&acc)[NB][8][4], int tx) {
-  // A -> As[buf] + ty*8 ; B -> Bs[buf][0]
+// FP64 tensor-core inner product: mma.sync.aligned.m8n8k4 (SASS DMMA.8x8x4).  On B200 DMMA
+// and DFMA share one FP64 pipe (37.1 vs 36.3 TF/s measured, 35.7 together), but one DMMA
+// retires 256 FMAs per issue slot, so the pipe can be kept busy with far fewer instructions
+// and shared-memory reads than the 8x4 register-tiled DFMA loop it replaces (measured 16 TF/s).
+// Fragments (PTX ISA, .f64 m8n8k4): g = lane>>2, t = lane&3;  A[g][t], B[t][g], C[g][2t..2t+1].
+// CTA tile 128 x 64, 8 warps as 4 (M) x 2 (N), warp tile 32 x 32 = 4 x 4 mma tiles.
+constexpr int LDA = BM + 4;   // k-row strides = 8 banks mod 32: conflict-free fragment loads
+constexpr int LDB = BN + 4;
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void tile_mma(const double* __restrict__ A, const double* __restrict__ B,
+                                         double (&acc)[4][4][2], int g, int t) {
+  // A -> As[buf] + wm*32 ; B -> Bs[buf] + wn*32
 #pragma unroll
-  for (int k = 0; k < BK; ++k) {
-    double a[8];
-    const double2* ap = reinterpret_cast<const double2*>(A + k * BM);
+  for (int k4 = 0; k4 < BK / 4; ++k4) {
+    double af[4], bf[4];
+    const double* ap = A + (k4 * 4 + t) * LDA + g;
+    const double* bp = B + (k4 * 4 + t) * LDB + g;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      double2 v = ap[i];
-      a[2 * i] = v.x;
-      a[2 * i + 1] = v.y;
+      af[i] = ap[i * 8];
+      bf[i] = bp[i * 8];
     }
 #pragma unroll
-    for (int q = 0; q < NB; ++q) {
-      const double* bp = B + (q * BK + k) * BN;
-      double2 b01 = *reinterpret_cast<const double2*>(bp + tx * 2);
-      double2 b23 = *reinterpret_cast<const double2*>(bp + 32 + tx * 2);
-      double b[4] = {b01.x, b01.y, b23.x, b23.y};
+    for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[q][i][j] = fma(a[i], b[j], acc[q][i][j]);
-    }
+      for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
   }
 }
 
-__device__ __forceinline__ int tile_col(int tx, int jj) { return (jj < 2) ? (tx * 2 + jj) : (32 + tx * 2 + (jj - 2)); }
+// Khatri-Rao weights of one row: S=2 -> (f1_0, f1_1); S=4 -> f1_s * f2_q at p = s*2+q
+template <int S>
+__device__ __forceinline__ void kr_weights(const double* __restrict__ f1, const double* __restrict__ f2, long img,
+                                           double (&w)[S]) {
+  const double a0 = f1[img * 2], a1 = f1[img * 2 + 1];
+  if (S == 2) {
+    w[0] = a0;
+    w[1] = a1;
+  } else {
+    const double b0 = f2[img * 2], b1 = f2[img * 2 + 1];
+    w[0] = a0 * b0;
+    w[1] = a0 * b1;
+    w[S - 2] = a1 * b0;
+    w[S - 1] = a1 * b1;
+  }
+}
 
 // ---------------------------------------------------------------------------
-template <int NB>
-__global__ void __launch_bounds__(NTHR)
-krgemm_kernel(const double* __restrict__ In, long ldin, int ma, const double* __restrict__ f1, int div,
-              const double* __restrict__ Bm0, const double* __restrict__ Bm1, long ldb, int J,
-              const double* __restrict__ f2, double* __restrict__ Out, long ldout, long rows) {
+// Out[row][j] = sum_{a,p} In[row][a] * w_p(row) * Bm[(a*S+p)*ldb + j].  K = S*ma.
+// 128(bm) x 64 tile per CTA, 8x4 per thread, two CTAs per SM; `bm` (rows per tile, <= 128)
+// is chosen by the host so that the tile count is a whole number of waves.
+template <int S>
+__global__ void __launch_bounds__(NTHR, 2)
+krgemm_kernel(const double* __restrict__ In, long ldin, int ma, const double* __restrict__ f1,
+              const double* __restrict__ f2, int div, const double* __restrict__ Bm, long ldb, int J,
+              double* __restrict__ Out, long ldout, long rows, int bm) {
   extern __shared__ __align__(16) double smem[];
-  double* As = smem;                 // [2][BK][BM]
-  double* Bs = smem + 2 * BK * BM;   // [2][NB][BK][BN]
-  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
-  const long row0 = (long)blockIdx.x * BM;
+  double* As = smem;                  // [2][BK][LDA]
+  double* Bs = smem + 2 * BK * LDA;   // [2][BK][LDB]
+  constexpr int AK = BK / S;         // a-values per k-tile
+  constexpr int APT = AK / 2;        // a-values per loader thread (2 threads per row)
+  const int t = threadIdx.x;
+  const int lane = t & 31, wid = t >> 5, wm = wid & 3, wn = wid >> 2, g = lane >> 2, tq = lane & 3;
+  const long row0 = (long)blockIdx.x * bm;
   const int j0 = blockIdx.y * BN;
 
-  const int lrow = t >> 1, lah = (t & 1) * 4;
+  const int lrow = t >> 1, lah = (t & 1) * APT;
   const long grow = row0 + lrow;
-  const bool rok = grow < rows;
-  double fa0 = 0.0, fa1 = 0.0;
-  if (rok) {
-    long img = grow / div;
-    fa0 = f1[img * 2];
-    fa1 = f1[img * 2 + 1];
-  }
+  const bool rok = (grow < rows) && (lrow < bm);
+  double w[S];
+#pragma unroll
+  for (int p = 0; p < S; ++p) w[p] = 0.0;
+  if (rok) kr_weights<S>(f1, f2, grow / div, w);
   const int bk = t >> 4, bc = (t & 15) * 4;
 
-  double acc[NB][8][4];
+  double acc[4][4][2];
 #pragma unroll
-  for (int q = 0; q < NB; ++q)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[q][i][j] = 0.0;
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  double ra[4];
-  double rb[NB][4];
-  const int nk = (ma + 7) / 8;
+  double ra[APT];
+  double rb[4];
+  const int nk = (ma + AK - 1) / AK;
+  const int K2 = ma * S;
 
   auto gload = [&](int kt) {
-    const int a0 = kt * 8 + lah;
+    const int a0 = kt * AK + lah;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < APT; ++i) {
       int a = a0 + i;
       ra[i] = (rok && a < ma) ? In[grow * ldin + a] : 0.0;
     }
-    const int k2 = kt * 16 + bk;
-    const bool kok = k2 < 2 * ma;
+    const int k2 = kt * BK + bk;
+    const bool kok = k2 < K2;
 #pragma unroll
-    for (int q = 0; q < NB; ++q) {
-      const double* Bq = (q == 0) ? Bm0 : Bm1;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        int j = j0 + bc + i;
-        rb[q][i] = (kok && j < J) ? Bq[(long)k2 * ldb + j] : 0.0;
-      }
+    for (int i = 0; i < 4; ++i) {
+      int j = j0 + bc + i;
+      rb[i] = (kok && j < J) ? Bm[(long)k2 * ldb + j] : 0.0;
     }
   };
   auto sstore = [&](int buf) {
-    double* A = As + buf * BK * BM;
+    double* A = As + buf * BK * LDA;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int k = (lah + i) * 2;
-      A[k * BM + lrow] = ra[i] * fa0;
-      A[(k + 1) * BM + lrow] = ra[i] * fa1;
-    }
+    for (int i = 0; i < APT; ++i)
 #pragma unroll
-    for (int q = 0; q < NB; ++q) {
-      double* B = Bs + ((buf * NB + q) * BK + bk) * BN + bc;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) B[i] = rb[q][i];
-    }
+      for (int p = 0; p < S; ++p) A[((lah + i) * S + p) * LDA + lrow] = ra[i] * w[p];
+    double2* B = reinterpret_cast<double2*>(Bs + (buf * BK + bk) * LDB + bc);
+    B[0] = make_double2(rb[0], rb[1]);
+    B[1] = make_double2(rb[2], rb[3]);
   };
 
   gload(0);
   sstore(0);
   __syncthreads();
+  const bool active = (wm * 32 < bm);
   for (int kt = 0; kt < nk; ++kt) {
     const int buf = kt & 1;
     if (kt + 1 < nk) gload(kt + 1);
-    tile_fma<NB>(As + buf * BK * BM + ty * 8, Bs + buf * NB * BK * BN, acc, tx);
+    if (active) tile_mma(As + buf * BK * LDA + wm * 32, Bs + buf * BK * LDB + wn * 32, acc, g, tq);
     if (kt + 1 < nk) sstore(buf ^ 1);
     __syncthreads();
   }
-
+  if (!active) return;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    long r = row0 + ty * 8 + i;
-    if (r >= rows) continue;
-    double w0 = 1.0, w1 = 0.0;
-    if (NB == 2) {
-      long img = r / div;
-      w0 = f2[img * 2];
-      w1 = f2[img * 2 + 1];
-    }
+  for (int mi = 0; mi < 4; ++mi) {
+    const int lr = wm * 32 + mi * 8 + g;
+    const long r = row0 + lr;
+    if (r >= rows || lr >= bm) continue;
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      int j = j0 + tile_col(tx, jj);
-      if (j < J) {
-        double v = (NB == 2) ? fma(w1, acc[NB - 1][i][jj], w0 * acc[0][i][jj]) : acc[0][i][jj];
-        Out[r * ldout + j] = v;
-      }
+    for (int ni = 0; ni < 4; ++ni) {
+      const int j = j0 + wn * 32 + ni * 8 + 2 * tq;
+      if (j < J) Out[r * ldout + j] = acc[mi][ni][0];
+      if (j + 1 < J) Out[r * ldout + j + 1] = acc[mi][ni][1];
     }
   }
 }
 
-void krgemm(cudaStream_t st, int NB, const double* In, long ldin, int ma, const double* f1, int div,
-            const double* Bm0, const double* Bm1, long ldb, int J, const double* f2, double* Out,
-            long ldout, long rows) {
+void krgemm(cudaStream_t st, int S, const double* In, long ldin, int ma, const double* f1, const double* f2,
+            int div, const double* Bm, long ldb, int J, double* Out, long ldout, long rows, int num_sm) {
   if (rows <= 0 || J <= 0) return;
-  dim3 grid((unsigned)((rows + BM - 1) / BM), (unsigned)((J + BN - 1) / BN));
-  size_t sh = (size_t)(2 * BK * BM + 2 * NB * BK * BN) * sizeof(double);
+  const int coltiles = (J + BN - 1) / BN;
+  const long slots = 2L * num_sm;
+  long T = (rows * coltiles + slots * BM - 1) / (slots * BM);   // tiles per resident CTA slot at bm = 128
+  if (T < 1) T = 1;
+  long rowtiles = (slots * T + coltiles - 1) / coltiles;
+  long bm = (rows + rowtiles - 1) / rowtiles;
+  bm = ((bm + 7) / 8) * 8;
+  if (bm > BM) bm = BM;
+  if (bm < 8) bm = 8;
+  dim3 grid((unsigned)((rows + bm - 1) / bm), (unsigned)coltiles);
+  size_t sh = (size_t)(2 * BK * LDA + 2 * BK * LDB) * sizeof(double);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(krgemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(krgemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    cudaFuncSetAttribute(krgemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(krgemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr = true;
   }
-  if (NB == 1)
-    krgemm_kernel<1><<<grid, NTHR, sh, st>>>(In, ldin, ma, f1, div, Bm0, Bm1, ldb, J, f2, Out, ldout, rows);
+  if (S == 2)
+    krgemm_kernel<2><<<grid, NTHR, sh, st>>>(In, ldin, ma, f1, f2, div, Bm, ldb, J, Out, ldout, rows, (int)bm);
   else
-    krgemm_kernel<2><<<grid, NTHR, sh, st>>>(In, ldin, ma, f1, div, Bm0, Bm1, ldb, J, f2, Out, ldout, rows);
+    krgemm_kernel<4><<<grid, NTHR, sh, st>>>(In, ldin, ma, f1, f2, div, Bm, ldb, J, Out, ldout, rows, (int)bm);
 }
 
 // ---------------------------------------------------------------------------
-template <int NB>
-__global__ void __launch_bounds__(NTHR)
+// Gpart[split][(a*S+p)][j] = sum_{row in split} In[row][a] * w_p(row) * Z[row][j].  M = S*ma, K = rows.
+template <int S>
+__global__ void __launch_bounds__(NTHR, 2)
 krgram_kernel(const double* __restrict__ In, long ldin, int ma, const double* __restrict__ f1,
               const double* __restrict__ f2, const double* __restrict__ Z, long ldz, int J,
               double* __restrict__ Gpart, long rows, long rows_per_split) {
   extern __shared__ __align__(16) double smem[];
-  double* As = smem;                 // [2][BK][BM]   BM index = (a_local*2+s)
-  double* Bs = smem + 2 * BK * BM;   // [2][NB][BK][BN]
-  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
-  const int a0 = blockIdx.x * (BM / 2);
+  double* As = smem;                  // [2][BK][LDA]   column index = (a_local*S+p)
+  double* Bs = smem + 2 * BK * LDA;   // [2][BK][LDB]
+  constexpr int AM = BM / S;         // a-values per m-tile
+  constexpr int APT = AM / 16;       // a-values per loader thread (16 threads per row)
+  const int t = threadIdx.x;
+  const int lane = t & 31, wid = t >> 5, wm = wid & 3, wn = wid >> 2, g = lane >> 2, tq = lane & 3;
+  const int a0 = blockIdx.x * AM;
   const int j0 = blockIdx.y * BN;
   const long rbeg = (long)blockIdx.z * rows_per_split;
   const long rend = (rbeg + rows_per_split < rows) ? (rbeg + rows_per_split) : rows;
-  const int lrow = t >> 4, c4 = (t & 15) * 4;
+  const int lrow = t >> 4, ca = (t & 15) * APT, c4 = (t & 15) * 4;
 
-  double acc[NB][8][4];
+  double acc[4][4][2];
 #pragma unroll
-  for (int q = 0; q < NB; ++q)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[q][i][j] = 0.0;
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  double ra[4], rz[4], rf[4];  // rf: f1_0, f1_1, f2_0, f2_1
+  double ra[APT], rz[4], w[S];
   const long nrow = (rend > rbeg) ? (rend - rbeg) : 0;
   const int nk = (int)((nrow + BK - 1) / BK);
 
@@ -200,32 +220,29 @@ krgram_kernel(const double* __restrict__ In, long ldin, int ma, const double* __
     const long r = rbeg + (long)kt * BK + lrow;
     const bool ok = r < rend;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int a = a0 + c4 + i;
+    for (int i = 0; i < APT; ++i) {
+      int a = a0 + ca + i;
       ra[i] = (ok && a < ma) ? In[r * ldin + a] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
       int j = j0 + c4 + i;
       rz[i] = (ok && j < J) ? Z[r * ldz + j] : 0.0;
     }
-    rf[0] = ok ? f1[r * 2] : 0.0;
-    rf[1] = ok ? f1[r * 2 + 1] : 0.0;
-    if (NB == 2) {
-      rf[2] = ok ? f2[r * 2] : 0.0;
-      rf[3] = ok ? f2[r * 2 + 1] : 0.0;
-    } else {
-      rf[2] = 1.0;
-      rf[3] = 0.0;
-    }
+#pragma unroll
+    for (int p = 0; p < S; ++p) w[p] = 0.0;
+    if (ok) kr_weights<S>(f1, f2, r, w);
   };
   auto sstore = [&](int buf) {
-    double2* A = reinterpret_cast<double2*>(As + (buf * BK + lrow) * BM + c4 * 2);
+    double* A = As + (buf * BK + lrow) * LDA + ca * S;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) A[i] = make_double2(ra[i] * rf[0], ra[i] * rf[1]);
+    for (int i = 0; i < APT; ++i)
 #pragma unroll
-    for (int q = 0; q < NB; ++q) {
-      double2* B = reinterpret_cast<double2*>(Bs + ((buf * NB + q) * BK + lrow) * BN + c4);
-      B[0] = make_double2(rz[0] * rf[2 + q], rz[1] * rf[2 + q]);
-      B[1] = make_double2(rz[2] * rf[2 + q], rz[3] * rf[2 + q]);
-    }
+      for (int p = 0; p < S; p += 2)
+        *reinterpret_cast<double2*>(A + i * S + p) = make_double2(ra[i] * w[p], ra[i] * w[p + 1]);
+    double2* B = reinterpret_cast<double2*>(Bs + (buf * BK + lrow) * LDB + c4);
+    B[0] = make_double2(rz[0], rz[1]);
+    B[1] = make_double2(rz[2], rz[3]);
   };
 
   if (nk > 0) {
@@ -236,54 +253,54 @@ krgram_kernel(const double* __restrict__ In, long ldin, int ma, const double* __
   for (int kt = 0; kt < nk; ++kt) {
     const int buf = kt & 1;
     if (kt + 1 < nk) gload(kt + 1);
-    tile_fma<NB>(As + buf * BK * BM + ty * 8, Bs + buf * NB * BK * BN, acc, tx);
+    tile_mma(As + buf * BK * LDA + wm * 32, Bs + buf * BK * LDB + wn * 32, acc, g, tq);
     if (kt + 1 < nk) sstore(buf ^ 1);
     __syncthreads();
   }
 
-  const long M2 = 2L * ma;
-  double* Gp = Gpart + (long)blockIdx.z * (M2 * NB * J);
+  const long M2 = (long)S * ma;
+  double* Gp = Gpart + (long)blockIdx.z * (M2 * J);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    long m2 = (long)a0 * 2 + ty * 8 + i;
+  for (int mi = 0; mi < 4; ++mi) {
+    const long m2 = (long)a0 * S + wm * 32 + mi * 8 + g;
     if (m2 >= M2) continue;
 #pragma unroll
-    for (int q = 0; q < NB; ++q)
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        int j = j0 + tile_col(tx, jj);
-        if (j < J) Gp[(m2 * NB + q) * J + j] = acc[q][i][jj];
-      }
+    for (int ni = 0; ni < 4; ++ni) {
+      const int j = j0 + wn * 32 + ni * 8 + 2 * tq;
+      if (j < J) Gp[m2 * J + j] = acc[mi][ni][0];
+      if (j + 1 < J) Gp[m2 * J + j + 1] = acc[mi][ni][1];
+    }
   }
 }
 
-int krgram_splits(int ma, int J, int NB, long rows, int num_sm) {
-  int mt = (2 * ma + BM - 1) / BM, nt = (J + BN - 1) / BN;
+int krgram_splits(int ma, int S, int J, long rows, int num_sm) {
+  int mt = (S * ma + BM - 1) / BM, nt = (J + BN - 1) / BN;
   long tiles = (long)mt * nt;
-  int s = (int)((2L * num_sm + tiles - 1) / tiles);
-  long maxs = (rows + 8 * BK - 1) / (8 * BK);  // at least 128 rows per split
+  int s = (int)((2L * num_sm) / tiles);           // one full wave of two CTAs per SM
+  if (s < 1) s = 1;
+  long maxs = (rows + 8 * BK - 1) / (8 * BK);     // at least 128 rows per split
   if (s > maxs) s = (int)maxs;
   if (s < 1) s = 1;
   if (s > 65535) s = 65535;
   return s;
 }
 
-void krgram(cudaStream_t st, int NB, const double* In, long ldin, int ma, const double* f1,
-            const double* f2, const double* Z, long ldz, int J, double* Gpart, long rows, int nsplit) {
-  dim3 grid((unsigned)((2 * ma + BM - 1) / BM), (unsigned)((J + BN - 1) / BN), (unsigned)nsplit);
+void krgram(cudaStream_t st, int S, const double* In, long ldin, int ma, const double* f1, const double* f2,
+            const double* Z, long ldz, int J, double* Gpart, long rows, int nsplit) {
+  dim3 grid((unsigned)((S * ma + BM - 1) / BM), (unsigned)((J + BN - 1) / BN), (unsigned)nsplit);
   long rps = (rows + nsplit - 1) / nsplit;
   rps = ((rps + BK - 1) / BK) * BK;
-  size_t sh = (size_t)(2 * BK * BM + 2 * NB * BK * BN) * sizeof(double);
+  size_t sh = (size_t)(2 * BK * LDA + 2 * BK * LDB) * sizeof(double);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(krgram_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(krgram_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    cudaFuncSetAttribute(krgram_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(krgram_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr = true;
   }
-  if (NB == 1)
-    krgram_kernel<1><<<grid, NTHR, sh, st>>>(In, ldin, ma, f1, f2, Z, ldz, J, Gpart, rows, rps);
-  else
+  if (S == 2)
     krgram_kernel<2><<<grid, NTHR, sh, st>>>(In, ldin, ma, f1, f2, Z, ldz, J, Gpart, rows, rps);
+  else
+    krgram_kernel<4><<<grid, NTHR, sh, st>>>(In, ldin, ma, f1, f2, Z, ldz, J, Gpart, rows, rps);
 }
 
 __global__ void reduce_partials_kernel(const double* __restrict__ Gpart, int nsplit, long n,

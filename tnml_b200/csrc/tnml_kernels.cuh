@@ -11,21 +11,20 @@ namespace tnml {
 constexpr int NL = 10;
 
 // ---- Khatri-Rao GEMM family -------------------------------------------------
-// krgemm: Out[row][j] = sum_q w_q(row) * sum_{a,s} In[row][a]*f1[img(row)][s] * Bm_q[(a*2+s)*ldb + j]
-//   img(row) = row / div ; NB = 1: w_0 = 1 ; NB = 2: w_q = f2[img(row)*2+q]
+// krgemm: Out[row][j] = sum_{a,p} In[row][a] * w_p(img(row)) * Bm[(a*S+p)*ldb + j],  img(row) = row/div
+//   S = 2: w = (f1_0, f1_1) ; S = 4: w_{s*2+q} = f1_s * f2_q.  K = S*ma; the Khatri-Rao operand
+//   l_n (x) phi_n (x) phi'_n is generated while it is staged.
 // Used for: projected input Q (fixedL.cc:318,377,399,416 restructured) and
 // environment advance (fixedL.cc:144-150, 221-229).
-void krgemm(cudaStream_t st, int NB, const double* In, long ldin, int ma, const double* f1, int div,
-            const double* Bm0, const double* Bm1, long ldb, int J, const double* f2, double* Out,
-            long ldout, long rows);
+void krgemm(cudaStream_t st, int S, const double* In, long ldin, int ma, const double* f1, const double* f2,
+            int div, const double* Bm, long ldb, int J, double* Out, long ldout, long rows, int num_sm);
 
-// krgram: Gpart[split][(a*2+s)][q][j] = sum_{row in split} In[row][a]*f1[row][s]*f2[row][q]*Z[row][j]
-// (NB = 1: f2 == nullptr, weight 1).  The rank-1 gradient accumulation of
-// fixedL.cc:379,418 as one K=NT contraction, split-K over CTAs, partials
-// reduced in a fixed order (deterministic).  Returns the number of splits.
-int krgram_splits(int ma, int J, int NB, long rows, int num_sm);
-void krgram(cudaStream_t st, int NB, const double* In, long ldin, int ma, const double* f1,
-            const double* f2, const double* Z, long ldz, int J, double* Gpart, long rows, int nsplit);
+// krgram: Gpart[split][(a*S+p)][j] = sum_{row in split} In[row][a] * w_p(row) * Z[row][j]
+// The rank-1 gradient accumulation of fixedL.cc:379,418 as one K=NT contraction, split-K over
+// CTAs, partials reduced in a fixed order (deterministic).
+int krgram_splits(int ma, int S, int J, long rows, int num_sm);
+void krgram(cudaStream_t st, int S, const double* In, long ldin, int ma, const double* f1, const double* f2,
+            const double* Z, long ldz, int J, double* Gpart, long rows, int nsplit);
 // G[i] = sum_split Gpart[split][i]   (+ optional: G[i] -= lambda*B[i])
 void reduce_partials(cudaStream_t st, const double* Gpart, int nsplit, long n, double* G);
 
