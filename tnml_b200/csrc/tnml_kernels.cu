@@ -22,7 +22,8 @@ constexpr int NTHR = 256;
 // retires 256 FMAs per issue slot, so the pipe can be kept busy with far fewer instructions
 // and shared-memory reads than the 8x4 register-tiled DFMA loop it replaces (measured 16 TF/s).
 // Fragments (PTX ISA, .f64 m8n8k4): g = lane>>2, t = lane&3;  A[g][t], B[t][g], C[g][2t..2t+1].
-// CTA tile 128 x 64, 8 warps as 4 (M) x 2 (N), warp tile 32 x 32 = 4 x 4 mma tiles.
+// CTA tile 128 x 64, 8 warps stacked along M, warp tile 16 x 64 = 2 x 8 mma tiles (16-row
+// granularity lets the host pick the rows per tile that balances the waves).
 constexpr int LDA = BM + 4;   // k-row strides = 8 banks mod 32: conflict-free fragment loads
 constexpr int LDB = BN + 4;
 
@@ -33,22 +34,21 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 }
 
 __device__ __forceinline__ void tile_mma(const double* __restrict__ A, const double* __restrict__ B,
-                                         double (&acc)[4][4][2], int g, int t) {
-  // A -> As[buf] + wm*32 ; B -> Bs[buf] + wn*32
+                                         double (&acc)[2][8][2], int g, int t) {
+  // A -> As[buf] + wm*16 ; B -> Bs[buf].  Warp tile 16 (M) x 64 (N) = 2 x 8 mma tiles.
 #pragma unroll
   for (int k4 = 0; k4 < BK / 4; ++k4) {
-    double af[4], bf[4];
+    double af[2], bf[8];
     const double* ap = A + (k4 * 4 + t) * LDA + g;
     const double* bp = B + (k4 * 4 + t) * LDB + g;
+    af[0] = ap[0];
+    af[1] = ap[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      af[i] = ap[i * 8];
-      bf[i] = bp[i * 8];
-    }
+    for (int i = 0; i < 8; ++i) bf[i] = bp[i * 8];
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
+    for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+      for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
   }
 }
 
@@ -84,7 +84,7 @@ krgemm_kernel(const double* __restrict__ In, long ldin, int ma, const double* __
   constexpr int AK = BK / S;         // a-values per k-tile
   constexpr int APT = AK / 2;        // a-values per loader thread (2 threads per row)
   const int t = threadIdx.x;
-  const int lane = t & 31, wid = t >> 5, wm = wid & 3, wn = wid >> 2, g = lane >> 2, tq = lane & 3;
+  const int lane = t & 31, wm = t >> 5, g = lane >> 2, tq = lane & 3;
   const long row0 = (long)blockIdx.x * bm;
   const int j0 = blockIdx.y * BN;
 
@@ -97,11 +97,11 @@ krgemm_kernel(const double* __restrict__ In, long ldin, int ma, const double* __
   if (rok) kr_weights<S>(f1, f2, grow / div, w);
   const int bk = t >> 4, bc = (t & 15) * 4;
 
-  double acc[4][4][2];
+  double acc[2][8][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   double ra[APT];
   double rb[4];
@@ -137,23 +137,23 @@ krgemm_kernel(const double* __restrict__ In, long ldin, int ma, const double* __
   gload(0);
   sstore(0);
   __syncthreads();
-  const bool active = (wm * 32 < bm);
+  const bool active = (wm * 16 < bm);
   for (int kt = 0; kt < nk; ++kt) {
     const int buf = kt & 1;
     if (kt + 1 < nk) gload(kt + 1);
-    if (active) tile_mma(As + buf * BK * LDA + wm * 32, Bs + buf * BK * LDB + wn * 32, acc, g, tq);
+    if (active) tile_mma(As + buf * BK * LDA + wm * 16, Bs + buf * BK * LDB, acc, g, tq);
     if (kt + 1 < nk) sstore(buf ^ 1);
     __syncthreads();
   }
   if (!active) return;
 #pragma unroll
-  for (int mi = 0; mi < 4; ++mi) {
-    const int lr = wm * 32 + mi * 8 + g;
+  for (int mi = 0; mi < 2; ++mi) {
+    const int lr = wm * 16 + mi * 8 + g;
     const long r = row0 + lr;
     if (r >= rows || lr >= bm) continue;
 #pragma unroll
-    for (int ni = 0; ni < 4; ++ni) {
-      const int j = j0 + wn * 32 + ni * 8 + 2 * tq;
+    for (int ni = 0; ni < 8; ++ni) {
+      const int j = j0 + ni * 8 + 2 * tq;
       if (j < J) Out[r * ldout + j] = acc[mi][ni][0];
       if (j + 1 < J) Out[r * ldout + j + 1] = acc[mi][ni][1];
     }
@@ -164,14 +164,18 @@ void krgemm(cudaStream_t st, int S, const double* In, long ldin, int ma, const d
             int div, const double* Bm, long ldb, int J, double* Out, long ldout, long rows, int num_sm) {
   if (rows <= 0 || J <= 0) return;
   const int coltiles = (J + BN - 1) / BN;
-  const long slots = 2L * num_sm;
-  long T = (rows * coltiles + slots * BM - 1) / (slots * BM);   // tiles per resident CTA slot at bm = 128
-  if (T < 1) T = 1;
-  long rowtiles = (slots * T + coltiles - 1) / coltiles;
-  long bm = (rows + rowtiles - 1) / rowtiles;
-  bm = ((bm + 7) / 8) * 8;
-  if (bm > BM) bm = BM;
-  if (bm < 8) bm = 8;
+  // rows per tile (multiple of the 16-row warp tile): minimise the makespan
+  // ceil(tiles / SMs) * (bm + fixed per-tile overhead) -- the FP64 pipe is the bottleneck, so an
+  // SM's time is the sum of the rows it is handed
+  long bm = BM, best = -1;
+  for (long cand = BM; cand >= 32; cand -= 16) {
+    long tiles = ((rows + cand - 1) / cand) * coltiles;
+    long cost = ((tiles + num_sm - 1) / num_sm) * (cand + 6);
+    if (best < 0 || cost < best) {
+      best = cost;
+      bm = cand;
+    }
+  }
   dim3 grid((unsigned)((rows + bm - 1) / bm), (unsigned)coltiles);
   size_t sh = (size_t)(2 * BK * LDA + 2 * BK * LDB) * sizeof(double);
   static bool attr = false;
@@ -199,18 +203,18 @@ krgram_kernel(const double* __restrict__ In, long ldin, int ma, const double* __
   constexpr int AM = BM / S;         // a-values per m-tile
   constexpr int APT = AM / 16;       // a-values per loader thread (16 threads per row)
   const int t = threadIdx.x;
-  const int lane = t & 31, wid = t >> 5, wm = wid & 3, wn = wid >> 2, g = lane >> 2, tq = lane & 3;
+  const int lane = t & 31, wm = t >> 5, g = lane >> 2, tq = lane & 3;
   const int a0 = blockIdx.x * AM;
   const int j0 = blockIdx.y * BN;
   const long rbeg = (long)blockIdx.z * rows_per_split;
   const long rend = (rbeg + rows_per_split < rows) ? (rbeg + rows_per_split) : rows;
   const int lrow = t >> 4, ca = (t & 15) * APT, c4 = (t & 15) * 4;
 
-  double acc[4][4][2];
+  double acc[2][8][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   double ra[APT], rz[4], w[S];
   const long nrow = (rend > rbeg) ? (rend - rbeg) : 0;
@@ -234,12 +238,14 @@ krgram_kernel(const double* __restrict__ In, long ldin, int ma, const double* __
     if (ok) kr_weights<S>(f1, f2, r, w);
   };
   auto sstore = [&](int buf) {
-    double* A = As + (buf * BK + lrow) * LDA + ca * S;
+    // shared-memory column index = p*AM + a_local (p-major): consecutive lanes write
+    // consecutive 16-byte words (the a-major order gave 8-way bank conflicts)
+    double* A = As + (buf * BK + lrow) * LDA + ca;
 #pragma unroll
-    for (int i = 0; i < APT; ++i)
+    for (int p = 0; p < S; ++p)
 #pragma unroll
-      for (int p = 0; p < S; p += 2)
-        *reinterpret_cast<double2*>(A + i * S + p) = make_double2(ra[i] * w[p], ra[i] * w[p + 1]);
+      for (int i = 0; i < APT; i += 2)
+        *reinterpret_cast<double2*>(A + p * AM + i) = make_double2(ra[i] * w[p], ra[i + 1] * w[p]);
     double2* B = reinterpret_cast<double2*>(Bs + (buf * BK + lrow) * LDB + c4);
     B[0] = make_double2(rz[0], rz[1]);
     B[1] = make_double2(rz[2], rz[3]);
@@ -253,7 +259,7 @@ krgram_kernel(const double* __restrict__ In, long ldin, int ma, const double* __
   for (int kt = 0; kt < nk; ++kt) {
     const int buf = kt & 1;
     if (kt + 1 < nk) gload(kt + 1);
-    tile_mma(As + buf * BK * LDA + wm * 32, Bs + buf * BK * LDB + wn * 32, acc, g, tq);
+    tile_mma(As + buf * BK * LDA + wm * 16, Bs + buf * BK * LDB, acc, g, tq);
     if (kt + 1 < nk) sstore(buf ^ 1);
     __syncthreads();
   }
@@ -261,12 +267,14 @@ krgram_kernel(const double* __restrict__ In, long ldin, int ma, const double* __
   const long M2 = (long)S * ma;
   double* Gp = Gpart + (long)blockIdx.z * (M2 * J);
 #pragma unroll
-  for (int mi = 0; mi < 4; ++mi) {
-    const long m2 = (long)a0 * S + wm * 32 + mi * 8 + g;
-    if (m2 >= M2) continue;
+  for (int mi = 0; mi < 2; ++mi) {
+    const int ml = wm * 16 + mi * 8 + g;          // p-major local column
+    const int pp = ml / AM, al = ml - pp * AM;
+    if (a0 + al >= ma) continue;
+    const long m2 = (long)(a0 + al) * S + pp;
 #pragma unroll
-    for (int ni = 0; ni < 4; ++ni) {
-      const int j = j0 + wn * 32 + ni * 8 + 2 * tq;
+    for (int ni = 0; ni < 8; ++ni) {
+      const int j = j0 + ni * 8 + 2 * tq;
       if (j < J) Gp[m2 * J + j] = acc[mi][ni][0];
       if (j + 1 < J) Gp[m2 * J + j + 1] = acc[mi][ni][1];
     }
@@ -323,14 +331,19 @@ __device__ __forceinline__ double warp_allsum(double v) {
   return v;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(256)
+// MCH = ceil(m/32) <= 4: the image's whole fat environment (10 x m doubles) is loaded with
+// all loads in flight at once and stays in registers for the backward contraction (one HBM
+// read per image; the loop version below issued 11 loads per round trip and re-read F).
+// MCH = 0: generic loop version for m > 128.
+template <int MODE, int MCH>
+__global__ void __launch_bounds__(128, (MCH > 0) ? 3 : 4)
 fat_kernel_t(const double* __restrict__ Q, const double* __restrict__ F, int m,
              const int32_t* __restrict__ labels, double* __restrict__ P, double* __restrict__ Z,
              int32_t* __restrict__ pred, double* __restrict__ stats_partial, long NT) {
+  constexpr int WPB = 4;  // warps per block
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long gw = (long)blockIdx.x * 8 + warp;
-  const long nw = (long)gridDim.x * 8;
+  const long gw = (long)blockIdx.x * WPB + warp;
+  const long nw = (long)gridDim.x * WPB;
   double cst[NL];
 #pragma unroll
   for (int l = 0; l < NL; ++l) cst[l] = 0.0;
@@ -342,13 +355,34 @@ fat_kernel_t(const double* __restrict__ Q, const double* __restrict__ F, int m,
     double pl[NL];
 #pragma unroll
     for (int l = 0; l < NL; ++l) pl[l] = 0.0;
-    for (int f = lane; f < m; f += 32) {
-      double qv = q[f];
+    constexpr int C = (MCH > 0) ? MCH : 1;
+    double qv[C];
+    double fv[NL][C];
+    if (MCH > 0) {
 #pragma unroll
-      for (int l = 0; l < NL; ++l) pl[l] = fma(qv, Fn[(long)l * m + f], pl[l]);
+      for (int c = 0; c < C; ++c) {
+        const int f = lane + 32 * c;
+        const bool ok = f < m;
+        qv[c] = ok ? q[f] : 0.0;
+#pragma unroll
+        for (int l = 0; l < NL; ++l) fv[l][c] = ok ? Fn[(long)l * m + f] : 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int l = 0; l < NL; ++l) pl[l] = fma(qv[c], fv[l][c], pl[l]);
+    } else {
+      for (int f = lane; f < m; f += 32) {
+        double x = q[f];
+#pragma unroll
+        for (int l = 0; l < NL; ++l) pl[l] = fma(x, Fn[(long)l * m + f], pl[l]);
+      }
     }
 #pragma unroll
-    for (int l = 0; l < NL; ++l) pl[l] = warp_allsum(pl[l]);
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int l = 0; l < NL; ++l) pl[l] += __shfl_xor_sync(0xffffffffu, pl[l], o);
+    }
     if (P != nullptr) {
       double mine = 0.0;
 #pragma unroll
@@ -383,23 +417,45 @@ fat_kernel_t(const double* __restrict__ Q, const double* __restrict__ F, int m,
       for (int l = 0; l < NL; ++l) cst[l] += (l == lab) ? e : 0.0;
       if (MODE == FAT_GRAD) {
         double* z = Z + n * m;
-        for (int f = lane; f < m; f += 32) {
-          double s = 0.0;
+        if (MCH > 0) {
 #pragma unroll
-          for (int l = 0; l < NL; ++l) s = fma(dp[l], Fn[(long)l * m + f], s);
-          z[f] = s;
+          for (int c = 0; c < C; ++c) {
+            const int f = lane + 32 * c;
+            double sacc = 0.0;
+#pragma unroll
+            for (int l = 0; l < NL; ++l) sacc = fma(dp[l], fv[l][c], sacc);
+            if (f < m) z[f] = sacc;
+          }
+        } else {
+          for (int f = lane; f < m; f += 32) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int l = 0; l < NL; ++l) sacc = fma(dp[l], Fn[(long)l * m + f], sacc);
+            z[f] = sacc;
+          }
         }
       } else if (MODE == FAT_GRAD_OUTER) {
         double* z = Z + n * (long)NL * m;
-        for (int f = lane; f < m; f += 32) {
-          double qv = q[f];
+        if (MCH > 0) {
 #pragma unroll
-          for (int l = 0; l < NL; ++l) z[(long)l * m + f] = dp[l] * qv;
+          for (int c = 0; c < C; ++c) {
+            const int f = lane + 32 * c;
+            if (f < m) {
+#pragma unroll
+              for (int l = 0; l < NL; ++l) z[(long)l * m + f] = dp[l] * qv[c];
+            }
+          }
+        } else {
+          for (int f = lane; f < m; f += 32) {
+            double x = q[f];
+#pragma unroll
+            for (int l = 0; l < NL; ++l) z[(long)l * m + f] = dp[l] * x;
+          }
         }
       }
     }
   }
-  __shared__ double red[8][12];
+  __shared__ double red[WPB][12];
   if (lane == 0) {
 #pragma unroll
     for (int l = 0; l < NL; ++l) red[warp][l] = cst[l];
@@ -410,27 +466,43 @@ fat_kernel_t(const double* __restrict__ Q, const double* __restrict__ F, int m,
   if (threadIdx.x < 16) {
     double s = 0.0;
     if (threadIdx.x < 12)
-      for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+      for (int w = 0; w < WPB; ++w) s += red[w][threadIdx.x];
     stats_partial[(long)blockIdx.x * 16 + threadIdx.x] = s;
   }
 }
 
-int fat_blocks(int num_sm) { return num_sm * 8; }
+int fat_blocks(int num_sm) { return num_sm * 12; }
+
+template <int MODE>
+static void fat_launch(cudaStream_t st, const double* Q, const double* F, int m, const int32_t* labels, double* P,
+                       double* Z, int32_t* pred, double* sp, int nb, long NT) {
+  const int mch = (m + 31) / 32;
+  if (mch == 1)
+    fat_kernel_t<MODE, 1><<<nb, 128, 0, st>>>(Q, F, m, labels, P, Z, pred, sp, NT);
+  else if (mch == 2)
+    fat_kernel_t<MODE, 2><<<nb, 128, 0, st>>>(Q, F, m, labels, P, Z, pred, sp, NT);
+  else if (mch == 3)
+    fat_kernel_t<MODE, 3><<<nb, 128, 0, st>>>(Q, F, m, labels, P, Z, pred, sp, NT);
+  else if (mch == 4)
+    fat_kernel_t<MODE, 4><<<nb, 128, 0, st>>>(Q, F, m, labels, P, Z, pred, sp, NT);
+  else
+    fat_kernel_t<MODE, 0><<<nb, 128, 0, st>>>(Q, F, m, labels, P, Z, pred, sp, NT);
+}
 
 void fat_kernel(cudaStream_t st, int mode, const double* Q, const double* F, int m, const int32_t* labels,
                 double* P, double* Z, int32_t* pred, double* stats_partial, int nblocks, long NT) {
   switch (mode) {
     case FAT_GRAD:
-      fat_kernel_t<FAT_GRAD><<<nblocks, 256, 0, st>>>(Q, F, m, labels, P, Z, pred, stats_partial, NT);
+      fat_launch<FAT_GRAD>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
       break;
     case FAT_PAP:
-      fat_kernel_t<FAT_PAP><<<nblocks, 256, 0, st>>>(Q, F, m, labels, P, Z, pred, stats_partial, NT);
+      fat_launch<FAT_PAP>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
       break;
     case FAT_COST:
-      fat_kernel_t<FAT_COST><<<nblocks, 256, 0, st>>>(Q, F, m, labels, P, Z, pred, stats_partial, NT);
+      fat_launch<FAT_COST>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
       break;
     default:
-      fat_kernel_t<FAT_GRAD_OUTER><<<nblocks, 256, 0, st>>>(Q, F, m, labels, P, Z, pred, stats_partial, NT);
+      fat_launch<FAT_GRAD_OUTER>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
       break;
   }
 }

@@ -621,14 +621,15 @@ qr_block_kernel(double* __restrict__ X, int nb, int ns, double* __restrict__ tau
   //      no per-element guards are needed).  Waiting warps back off with nanosleep so that
   //      the pivot warp owns the issue slots and the shared-memory pipe.
   for (int kk = 0; kk < w; ++kk) {
-    if (lane == 0) {
-      unsigned ns_sleep = 32;
-      while (sflag[kk] == 0) {
-        __nanosleep(ns_sleep);
-        if (ns_sleep < 256) ns_sleep *= 2;
-      }
+    // Warp-uniform wait (every lane reads the flag, the vote result is uniform): a lane-0-only
+    // spin makes the warp divergent and the compiler then wraps every later __shfl_sync in
+    // WARPSYNC.COLLECTIVE, which cost ~4k cycles per pivot.  Only the next three pivot
+    // owners poll continuously, the others back off.
+    while (true) {
+      const int f = sflag[kk];
+      if (__all_sync(0xffffffffu, f != 0)) break;
+      if (kk < w - 3) __nanosleep(200);
     }
-    __syncwarp();
     __threadfence_block();
     if (kk == w - 1) t_a = clock64();   // the flag this warp's pivot was waiting for
     const double* vk = sv + (long)kk * nb;
@@ -679,7 +680,14 @@ qr_block_kernel(double* __restrict__ X, int nb, int ns, double* __restrict__ tau
     if (r < nb) svw[r] = (r < j) ? 0.0 : ((r == j) ? 1.0 : out);
   }
   if (lane == 0) stau[w] = tj;
-  // publish inside the CTA first: the pivot chain must not wait for the L2 round trip
+  // global copies are ISSUED before the cta-scope publication (they are not waited for), so
+  // that the batched gpu-scope fence of a later warp is cumulative over them
+#pragma unroll
+  for (int i = 0; i < RPL; ++i) {
+    int r = lane + 32 * i;
+    if (r < nb) __stcg(aj + r, outv[i]);
+  }
+  if (lane == 0) __stcg(tau + j, tj);
   __threadfence_block();
   __syncwarp();
   if (lane == 0) sflag[w] = 1;
@@ -691,15 +699,19 @@ qr_block_kernel(double* __restrict__ X, int nb, int ns, double* __restrict__ tau
     asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
     g_qr_dbg[j * 4 + 3] = sm;
   }
-#pragma unroll
-  for (int i = 0; i < RPL; ++i) {
-    int r = lane + 32 * i;
-    if (r < nb) __stcg(aj + r, outv[i]);
+  // Global publication in batches of 8 columns: a gpu-scope fence (MEMBAR.GL + L1
+  // invalidate) stalls the memory pipe of the whole SM for ~2 us; issued by every pivot warp
+  // it sat on the pivot chain (640 us per QR).  The last column of each batch fences once --
+  // the earlier columns of the batch were observed through the cta-scope flag chain, so the
+  // fence is cumulative over their stores (PTX memory model causality order).
+  const bool last_in_cta = (j == ns - 1) || (w == 31);
+  if ((w & 7) == 7 || last_in_cta) {
+    __threadfence_block();
+    __threadfence();
+    __syncwarp();
+    const int first = c0 + (w & ~7);
+    if (lane <= (w & 7)) ready[first + lane] = 1;
   }
-  if (lane == 0) __stcg(tau + j, tj);
-  __threadfence();
-  __syncwarp();
-  if (lane == 0) ready[j] = 1;
 }
 
 // M = R^T as a column-major ns x ns matrix: M[:, j] = row j of R (upper triangular)

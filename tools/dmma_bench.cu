@@ -25,20 +25,21 @@ __global__ void k(double* out, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 template <int MODE>
-void run(const char* name, double* o) {
+void run(const char* name, double* o, int bps = 4, int thr = 256) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  const int thr = 256, blocks = 148 * 4, iters = 20000;
+  const int blocks = 148 * bps, iters = 20000;
   k<MODE><<<blocks, thr>>>(o, 100); cudaDeviceSynchronize();
   cudaEventRecord(e0); k<MODE><<<blocks, thr>>>(o, iters); cudaEventRecord(e1); cudaDeviceSynchronize();
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   double warps = (double)blocks * thr / 32;
   double fl_mma = (MODE != 1) ? warps * iters * 8.0 * 512.0 : 0;
   double fl_fma = (MODE != 0) ? warps * iters * 8.0 * 64.0 : 0;
-  printf("%-12s %.3f ms  DMMA %.2f TF/s  DFMA %.2f TF/s  total %.2f TF/s\n", name, ms, fl_mma / ms / 1e9, fl_fma / ms / 1e9,
+  printf("%-12s (%d CTA/SM x %d thr) %.3f ms  DMMA %.2f TF/s  DFMA %.2f TF/s  total %.2f TF/s\n", name, ms, fl_mma / ms / 1e9, fl_fma / ms / 1e9,
          (fl_mma + fl_fma) / ms / 1e9);
 }
 int main() {
   double* o; cudaMalloc(&o, 148 * 4 * 256 * 8);
   run<0>("dmma only", o); run<1>("dfma only", o); run<2>("dmma+dfma", o);
+  run<0>("dmma only", o, 2, 256); run<0>("dmma only", o, 1, 256); run<0>("dmma only", o, 1, 128); run<0>("dmma only", o, 2, 128);
   return 0;
 }
