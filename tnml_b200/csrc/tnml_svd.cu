@@ -23,6 +23,9 @@ namespace tnml {
 
 constexpr int JW = 16;  // block width (columns)
 
+__device__ long long* g_qr_dbg = nullptr;   // optional [ns][4] clock64 stamps (TNML_QR_DEBUG)
+
+
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -319,6 +322,217 @@ jacobi_diag_smem_kernel(double* __restrict__ X, double* __restrict__ J, int nb, 
   if (lane == 0 && mo > 0.0) atomic_max_pos(info, mo);
 }
 
+
+// ---------------------------------------------------------------------------
+// Gram-based block Jacobi: one CTA per block pair (32 staged columns of [A | J]).
+//   1. G = A_blk^T A_blk (32 x 32) with FP64 tensor-core MMAs (DMMA.8x8x4)
+//   2. NR rounds of 16 disjoint plane rotations applied to G itself (G <- R^T G R, ping-pong
+//      buffers, one barrier per round) while the product of the rotations accumulates in RA;
+//      no dot products / warp shuffles inside the round chain
+//   3. [A | J]_blk <- [A | J]_blk * RA, again with DMMA, written back
+// Mathematically the same rotations as the column-wise kernel above (which is bound by
+// shared-memory bandwidth: every round re-reads and re-writes all 32 staged columns).
+__device__ __forceinline__ void dmma884s(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// Branch-free (two of them are evaluated per thread and must interleave).  rot = 1 when a
+// rotation is applied, 0 when the pair is already orthogonal to tolerance.
+__device__ __forceinline__ void plane_rot(double a, double b, double g, double tol2, double& c, double& s,
+                                          double& rot) {
+  const double ab = a * b, gg = g * g;
+  const bool doit = (ab > 0.0) && (gg > tol2 * ab);
+  const double d = b - a, h = 2.0 * g;
+  const double r2 = doit ? fma(d, d, h * h) : 1.0;
+  const double rinv = rsqrt(r2);
+  const double c2 = fma(0.5 * fabs(d), rinv, 0.5);
+  const double rc = rsqrt(c2);
+  const double cc = c2 * rc;
+  const double ss = copysign(0.5, d) * h * rinv * rc;
+  c = doit ? cc : 1.0;
+  s = doit ? ss : 0.0;
+  rot = doit ? 1.0 : 0.0;
+}
+
+constexpr int GLD = 36;   // leading dimension of the 32 x 32 Gram / rotation matrices in smem
+
+template <int NR>   // 31: all pairs of the 32 columns; 16: cross pairs only
+__global__ void __launch_bounds__(512)
+jacobi_gram_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows, int ns, int ld, int nblk_e, int R,
+                   double tol2, double* __restrict__ info, const int* __restrict__ flags) {
+  if (flags[0]) return;
+  extern __shared__ __align__(16) double sm[];
+  double* S = sm;                       // [32][ld]
+  double* G0 = sm + 32L * ld;           // [32][GLD]
+  double* G1 = G0 + 32 * GLD;
+  double* RA = G1 + 32 * GLD;
+  double* CS = RA + 32 * GLD;                                   // [16][2]
+  unsigned short* PQ = reinterpret_cast<unsigned short*>(CS + 32);   // [NR][16]  p | q << 8
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  int P, Q;
+  rr_pair(nblk_e, R, blockIdx.x, P, Q);
+  const int c0 = P * 16, c1 = Q * 16;
+  if (c0 >= ns && c1 >= ns) return;
+  const int tot = rows + ns;
+  long long tstamp[6];
+  tstamp[0] = clock64();
+  // ---- stage (invalid columns and the padding rows are zero).  Thread = (row pair rc,
+  //      column parity): 16 independent 16-byte loads in flight per thread, no index division.
+  const int rc2 = tid & 255, cpar = tid >> 8;
+  const int ld2 = ld >> 1, rows2 = rows >> 1, tot2 = tot >> 1;   // rows, ns are even (2m or 2m*NL)
+  if (rc2 < ld2) {
+    double2 v[16];
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const int k = cpar + 2 * it;
+      const int c = (k < 16) ? (c0 + k) : (c1 + k - 16);
+      v[it] = make_double2(0.0, 0.0);
+      if (c < ns && rc2 < tot2)
+        v[it] = (rc2 < rows2) ? __ldcg(reinterpret_cast<const double2*>(A + (long)c * rows) + rc2)
+                              : __ldcg(reinterpret_cast<const double2*>(Jm + (long)c * ns) + (rc2 - rows2));
+    }
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const int k = cpar + 2 * it;
+      reinterpret_cast<double2*>(S + (long)k * ld)[rc2] = v[it];
+    }
+  }
+  for (int i = tid; i < 32 * GLD; i += 512) RA[i] = ((i / GLD) == (i % GLD)) ? 1.0 : 0.0;
+  if (tid < NR * 16) {
+    const int rd = tid >> 4, k = tid & 15;
+    int p, q;
+    if (NR == 31) {
+      rr_pair(32, rd, k, p, q);
+    } else {
+      p = k;
+      q = 16 + ((k + rd) & 15);
+    }
+    PQ[tid] = (unsigned short)(p | (q << 8));
+  }
+  __syncthreads();
+  tstamp[1] = clock64();
+  // ---- Gram of the A part: warp (ti,tj) owns an 8 x 8 tile
+  {
+    const int ti = warp >> 2, tj = warp & 3;
+    const double* pa = S + (long)(ti * 8 + g) * ld + t;
+    const double* pb = S + (long)(tj * 8 + g) * ld + t;
+    double d0 = 0.0, d1 = 0.0;
+    for (int r0 = 0; r0 < rows; r0 += 4) {
+      const bool ok = (r0 + t) < rows;
+      const double a = ok ? pa[r0] : 0.0;
+      const double b = ok ? pb[r0] : 0.0;
+      dmma884s(d0, d1, a, b);
+    }
+    G0[(ti * 8 + g) * GLD + tj * 8 + 2 * t] = d0;
+    G0[(ti * 8 + g) * GLD + tj * 8 + 2 * t + 1] = d1;
+  }
+  __syncthreads();
+  tstamp[2] = clock64();
+  // ---- rotation rounds on the Gram matrix.  The loop is issue bound (512 threads), so each
+  //      rotation is computed once (lanes 0..15 of warp 0), then 256 threads update one 2x2
+  //      block of G each and the other 256 update RA.
+  double* cur = G0;
+  double* nxt = G1;
+  double mo = 0.0;
+  long long rs[5] = {0, 0, 0, 0, 0};
+  for (int rd = 0; rd < NR; ++rd) {
+    if (rd == 3) rs[0] = clock64();
+    if (tid < 16) {
+      const int pq = PQ[rd * 16 + tid];
+      const int p = pq & 0xff, q = pq >> 8;
+      double c, sn, rot;
+      plane_rot(cur[p * GLD + p], cur[q * GLD + q], cur[p * GLD + q], tol2, c, sn, rot);
+      CS[2 * tid] = c;
+      CS[2 * tid + 1] = sn;
+      mo = fmax(mo, rot);
+    }
+    if (rd == 3) rs[1] = clock64();
+    __syncthreads();
+    if (rd == 3) rs[2] = clock64();
+    if (tid < 256) {
+      const int k = tid >> 4, l = tid & 15;
+      const int pqk = PQ[rd * 16 + k], pql = PQ[rd * 16 + l];
+      const int pk = pqk & 0xff, qk = pqk >> 8, pl = pql & 0xff, ql = pql >> 8;
+      const double ck = CS[2 * k], sk = CS[2 * k + 1], cl = CS[2 * l], sl = CS[2 * l + 1];
+      const double g00 = cur[pk * GLD + pl], g01 = cur[pk * GLD + ql];
+      const double g10 = cur[qk * GLD + pl], g11 = cur[qk * GLD + ql];
+      // T = R_k^T * Gb ; Gb' = T * R_l   with R = [[c, s], [-s, c]]
+      const double t00 = ck * g00 - sk * g10, t01 = ck * g01 - sk * g11;
+      const double t10 = sk * g00 + ck * g10, t11 = sk * g01 + ck * g11;
+      nxt[pk * GLD + pl] = t00 * cl - t01 * sl;
+      nxt[pk * GLD + ql] = t00 * sl + t01 * cl;
+      nxt[qk * GLD + pl] = t10 * cl - t11 * sl;
+      nxt[qk * GLD + ql] = t10 * sl + t11 * cl;
+    } else {   // RA <- RA * R : row i, two of the 16 pairs per thread
+      const int u = tid - 256, i = u >> 3, l0 = (u & 7) * 2;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int pql = PQ[rd * 16 + l0 + e];
+        const int pl = pql & 0xff, ql = pql >> 8;
+        const double cl = CS[2 * (l0 + e)], sl = CS[2 * (l0 + e) + 1];
+        const double a = RA[i * GLD + pl], b = RA[i * GLD + ql];
+        RA[i * GLD + pl] = cl * a - sl * b;
+        RA[i * GLD + ql] = sl * a + cl * b;
+      }
+    }
+    if (rd == 3) rs[3] = clock64();
+    __syncthreads();
+    if (rd == 3) rs[4] = clock64();
+    double* tmp = cur;
+    cur = nxt;
+    nxt = tmp;
+  }
+  tstamp[3] = clock64();
+  // ---- apply the accumulated rotation to the staged rows, 8-row blocks per warp
+  const int nrb = (tot + 7) / 8;
+  for (int rb = warp; rb < nrb; rb += 16) {
+    const int r0 = rb * 8;
+    double acc[4][2];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) acc[n][0] = acc[n][1] = 0.0;
+#pragma unroll
+    for (int k0 = 0; k0 < 32; k0 += 4) {
+      const double a = S[(long)(k0 + t) * ld + r0 + g];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const double b = RA[(k0 + t) * GLD + n * 8 + g];
+        dmma884s(acc[n][0], acc[n][1], a, b);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      S[(long)(n * 8 + 2 * t) * ld + r0 + g] = acc[n][0];
+      S[(long)(n * 8 + 2 * t + 1) * ld + r0 + g] = acc[n][1];
+    }
+  }
+  __syncthreads();
+  tstamp[4] = clock64();
+  // ---- write back
+  if (rc2 < tot2) {
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const int k = cpar + 2 * it;
+      const int c = (k < 16) ? (c0 + k) : (c1 + k - 16);
+      if (c < ns) {
+        const double2 v = reinterpret_cast<const double2*>(S + (long)k * ld)[rc2];
+        if (rc2 < rows2)
+          __stcg(reinterpret_cast<double2*>(A + (long)c * rows) + rc2, v);
+        else
+          __stcg(reinterpret_cast<double2*>(Jm + (long)c * ns) + (rc2 - rows2), v);
+      }
+    }
+  }
+  if (tid < 16 && mo > 0.0) atomic_max_pos(info, mo);
+  if (g_qr_dbg != nullptr && tid == 0 && blockIdx.x == 0) {
+    tstamp[5] = clock64();
+    for (int i = 0; i < 6; ++i) g_qr_dbg[2048 + i] = tstamp[i];
+    for (int i = 0; i < 5; ++i) g_qr_dbg[2056 + i] = rs[i];
+  }
+}
+
 __global__ void jacobi_sweep_end_kernel(double* __restrict__ info, int* __restrict__ flags, double tol) {
   if (threadIdx.x == 0 && !flags[0]) {
     info[3] += 1.0;
@@ -545,8 +759,6 @@ qr_dataflow_kernel(double* __restrict__ X, int nb, int ns, double* __restrict__ 
 // columns travel through shared memory (the pivot chain k -> k+1 stays on one SM for 31 of 32
 // steps), reflectors of earlier CTAs come from global memory with batched flag polls (the
 // flags are monotone: ready[k] implies ready[k-1]) and one-step-ahead prefetch.
-__device__ long long* g_qr_dbg = nullptr;   // optional [ns][4] clock64 stamps (TNML_QR_DEBUG)
-
 template <int RPL>
 __global__ void __launch_bounds__(1024)
 qr_block_kernel(double* __restrict__ X, int nb, int ns, double* __restrict__ tau, volatile int* ready) {
@@ -867,13 +1079,38 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
     cudaFuncSetAttribute(jacobi_diag_smem_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  const int bw = Wd ? Wd : JW;
+  // Gram-based kernel: 32 staged columns of length rows+ns plus three 32 x 36 matrices
+  const int gld = ((rows + ns + 15) / 16) * 16 + 4;
+  const size_t need_gram = ((size_t)32 * gld + 3 * 32 * GLD + 32) * sizeof(double) + 31 * 16 * sizeof(unsigned short);
+  static int use_gram = -1;
+  if (use_gram < 0) {
+    const char* e = getenv("TNML_SVD_GRAM");
+    use_gram = e ? atoi(e) : 1;
+    cudaFuncSetAttribute(jacobi_gram_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(jacobi_gram_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  }
+  const bool gram = use_gram && need_gram <= 220 * 1024 && ns > 16 && gld <= 512 && (rows % 2 == 0) && (ns % 2 == 0);
+  const int bw = gram ? 16 : (Wd ? Wd : JW);
   const int nblk = (ns + bw - 1) / bw;
   const int nblk_e = (nblk % 2) ? nblk + 1 : nblk;
-  const double conv = Wd ? tol2 : tol;   // the smem kernels track off^2
+  const double conv = gram ? 0.5 : (Wd ? tol2 : tol);   // gram: 'a rotation happened' flag; smem kernels: off^2
   const int max_sweeps = 60;
   int hflag = 0;
   for (int sw = 0; sw < max_sweeps && !hflag; ++sw) {
+    if (gram) {
+      for (int R = 0; R < nblk_e - 1; ++R) {
+        jacobi_gram_kernel<31><<<nblk_e / 2, 512, need_gram, st>>>(A, Jm, rows, ns, gld, nblk_e, R, tol2, w.info,
+                                                                   w.flags);
+        nl += 1;
+      }
+      jacobi_sweep_end_kernel<<<1, 32, 0, st>>>(w.info, w.flags, conv);
+      nl += 1;
+      if (sw >= 2) {
+        if (cudaMemcpyAsync(&hflag, w.flags, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
+      }
+      continue;
+    }
     if (Wd == 16) {
       jacobi_diag_smem_kernel<16><<<nblk, 16 * 16, need16 / 2, st>>>(A, Jm, rows, ns, tol2, w.info, w.flags);
     } else if (Wd == 8) {
@@ -930,8 +1167,22 @@ static void launch_qr_block8(cudaStream_t st, SvdWork& w, int nb, int ns) {
     cudaStreamSynchronize(st);
     std::vector<long long> hd(ns * 4);
     cudaMemcpy(hd.data(), dbg, ns * 4 * sizeof(long long), cudaMemcpyDeviceToHost);
+    long long gs[6], rs[5];
+    cudaMemcpy(gs, dbg + 2048, sizeof(gs), cudaMemcpyDeviceToHost);
+    cudaMemcpy(rs, dbg + 2056, sizeof(rs), cudaMemcpyDeviceToHost);
+    {
+      FILE* fg = fopen("gpurun_out/gram_debug.txt", "w");
+      if (fg) {
+        fprintf(fg, "gram kernel phases (cycles): stage %lld gram %lld rounds %lld apply %lld store %lld\n", gs[1] - gs[0],
+                gs[2] - gs[1], gs[3] - gs[2], gs[4] - gs[3], gs[5] - gs[4]);
+        fprintf(fg, "round 3 (thread 0): rot %lld  bar1 %lld  update %lld  bar2 %lld\n", rs[1] - rs[0], rs[2] - rs[1],
+                rs[3] - rs[2], rs[4] - rs[3]);
+        fclose(fg);
+      }
+    }
     FILE* f = fopen("gpurun_out/qr_debug.txt", "w");
     if (f) {
+      fprintf(f, "(gram stamps are written by the LAST gram launch of the previous svd)\n");
       for (int jj = 0; jj < ns; ++jj)
         fprintf(f, "%d sm=%lld wait_end=%lld apply_end=%lld publish=%lld\n", jj, hd[jj * 4 + 3], hd[jj * 4 + 0], hd[jj * 4 + 1],
                 hd[jj * 4 + 2]);
