@@ -358,64 +358,65 @@ __device__ __forceinline__ void plane_rot(double a, double b, double g, double t
 
 constexpr int GLD = 36;   // leading dimension of the 32 x 32 Gram / rotation matrices in smem
 
-template <int NR>   // 31: all pairs of the 32 columns; 16: cross pairs only
-__global__ void __launch_bounds__(512)
+template <int W>   // block width: 2W staged columns, all (2W choose 2) pairs in 2W-1 rounds
+__global__ void __launch_bounds__(32 * W)
 jacobi_gram_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows, int ns, int ld, int nblk_e, int R,
                    double tol2, double* __restrict__ info, const int* __restrict__ flags) {
+  constexpr int NC = 2 * W;         // staged columns
+  constexpr int NR = NC - 1;        // rounds
+  constexpr int NTH = 32 * W;       // threads (512 / 256)
+  constexpr int CP = NTH / 256;     // column parities of the staging map
+  constexpr int NWARP = NTH / 32;
+  constexpr int TG = NC / 8;        // 8x8 tiles per side of the Gram matrix
   if (flags[0]) return;
   extern __shared__ __align__(16) double sm[];
-  double* S = sm;                       // [32][ld]
-  double* G0 = sm + 32L * ld;           // [32][GLD]
-  double* G1 = G0 + 32 * GLD;
-  double* RA = G1 + 32 * GLD;
-  double* CS = RA + 32 * GLD;                                   // [16][2]
-  unsigned short* PQ = reinterpret_cast<unsigned short*>(CS + 32);   // [NR][16]  p | q << 8
+  double* S = sm;                       // [NC][ld]
+  double* G0 = sm + (long)NC * ld;      // [NC][GLD]
+  double* G1 = G0 + NC * GLD;
+  double* RA = G1 + NC * GLD;
+  double* CS = RA + NC * GLD;                                        // [W][2]
+  unsigned short* PQ = reinterpret_cast<unsigned short*>(CS + 2 * W);   // [NR][W]  p | q << 8
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   int P, Q;
   rr_pair(nblk_e, R, blockIdx.x, P, Q);
-  const int c0 = P * 16, c1 = Q * 16;
+  const int c0 = P * W, c1 = Q * W;
   if (c0 >= ns && c1 >= ns) return;
   const int tot = rows + ns;
   long long tstamp[6];
   tstamp[0] = clock64();
-  // ---- stage (invalid columns and the padding rows are zero).  Thread = (row pair rc,
+  // ---- stage (invalid columns and the padding rows are zero).  Thread = (row pair rc2,
   //      column parity): 16 independent 16-byte loads in flight per thread, no index division.
   const int rc2 = tid & 255, cpar = tid >> 8;
   const int ld2 = ld >> 1, rows2 = rows >> 1, tot2 = tot >> 1;   // rows, ns are even (2m or 2m*NL)
   if (rc2 < ld2) {
-    double2 v[16];
+    double2 v[NC / CP];
 #pragma unroll
-    for (int it = 0; it < 16; ++it) {
-      const int k = cpar + 2 * it;
-      const int c = (k < 16) ? (c0 + k) : (c1 + k - 16);
+    for (int it = 0; it < NC / CP; ++it) {
+      const int k = cpar + CP * it;
+      const int c = (k < W) ? (c0 + k) : (c1 + k - W);
       v[it] = make_double2(0.0, 0.0);
       if (c < ns && rc2 < tot2)
         v[it] = (rc2 < rows2) ? __ldcg(reinterpret_cast<const double2*>(A + (long)c * rows) + rc2)
                               : __ldcg(reinterpret_cast<const double2*>(Jm + (long)c * ns) + (rc2 - rows2));
     }
 #pragma unroll
-    for (int it = 0; it < 16; ++it) {
-      const int k = cpar + 2 * it;
+    for (int it = 0; it < NC / CP; ++it) {
+      const int k = cpar + CP * it;
       reinterpret_cast<double2*>(S + (long)k * ld)[rc2] = v[it];
     }
   }
-  for (int i = tid; i < 32 * GLD; i += 512) RA[i] = ((i / GLD) == (i % GLD)) ? 1.0 : 0.0;
-  if (tid < NR * 16) {
-    const int rd = tid >> 4, k = tid & 15;
+  for (int i = tid; i < NC * GLD; i += NTH) RA[i] = ((i / GLD) == (i % GLD)) ? 1.0 : 0.0;
+  for (int i = tid; i < NR * W; i += NTH) {
+    const int rd = i / W, k = i - rd * W;
     int p, q;
-    if (NR == 31) {
-      rr_pair(32, rd, k, p, q);
-    } else {
-      p = k;
-      q = 16 + ((k + rd) & 15);
-    }
-    PQ[tid] = (unsigned short)(p | (q << 8));
+    rr_pair(NC, rd, k, p, q);
+    PQ[i] = (unsigned short)(p | (q << 8));
   }
   __syncthreads();
   tstamp[1] = clock64();
-  // ---- Gram of the A part: warp (ti,tj) owns an 8 x 8 tile
-  {
-    const int ti = warp >> 2, tj = warp & 3;
+  // ---- Gram of the A part with DMMA: 8 x 8 tiles, one per warp (warps beyond TG*TG idle)
+  if (warp < TG * TG) {
+    const int ti = warp / TG, tj = warp - ti * TG;
     const double* pa = S + (long)(ti * 8 + g) * ld + t;
     const double* pb = S + (long)(tj * 8 + g) * ld + t;
     double d0 = 0.0, d1 = 0.0;
@@ -430,17 +431,14 @@ jacobi_gram_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows, in
   }
   __syncthreads();
   tstamp[2] = clock64();
-  // ---- rotation rounds on the Gram matrix.  The loop is issue bound (512 threads), so each
-  //      rotation is computed once (lanes 0..15 of warp 0), then 256 threads update one 2x2
-  //      block of G each and the other 256 update RA.
+  // ---- rotation rounds on the Gram matrix: each rotation is computed once (W threads), then
+  //      W*W threads update one 2x2 block of G each (ping-pong) and NC*W/2 threads update RA
   double* cur = G0;
   double* nxt = G1;
   double mo = 0.0;
-  long long rs[5] = {0, 0, 0, 0, 0};
   for (int rd = 0; rd < NR; ++rd) {
-    if (rd == 3) rs[0] = clock64();
-    if (tid < 16) {
-      const int pq = PQ[rd * 16 + tid];
+    if (tid < W) {
+      const int pq = PQ[rd * W + tid];
       const int p = pq & 0xff, q = pq >> 8;
       double c, sn, rot;
       plane_rot(cur[p * GLD + p], cur[q * GLD + q], cur[p * GLD + q], tol2, c, sn, rot);
@@ -448,12 +446,10 @@ jacobi_gram_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows, in
       CS[2 * tid + 1] = sn;
       mo = fmax(mo, rot);
     }
-    if (rd == 3) rs[1] = clock64();
     __syncthreads();
-    if (rd == 3) rs[2] = clock64();
-    if (tid < 256) {
-      const int k = tid >> 4, l = tid & 15;
-      const int pqk = PQ[rd * 16 + k], pql = PQ[rd * 16 + l];
+    if (tid < W * W) {
+      const int k = tid / W, l = tid - k * W;
+      const int pqk = PQ[rd * W + k], pql = PQ[rd * W + l];
       const int pk = pqk & 0xff, qk = pqk >> 8, pl = pql & 0xff, ql = pql >> 8;
       const double ck = CS[2 * k], sk = CS[2 * k + 1], cl = CS[2 * l], sl = CS[2 * l + 1];
       const double g00 = cur[pk * GLD + pl], g01 = cur[pk * GLD + ql];
@@ -465,11 +461,11 @@ jacobi_gram_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows, in
       nxt[pk * GLD + ql] = t00 * sl + t01 * cl;
       nxt[qk * GLD + pl] = t10 * cl - t11 * sl;
       nxt[qk * GLD + ql] = t10 * sl + t11 * cl;
-    } else {   // RA <- RA * R : row i, two of the 16 pairs per thread
-      const int u = tid - 256, i = u >> 3, l0 = (u & 7) * 2;
+    } else if (tid < W * W + NC * W / 2) {   // RA <- RA * R : row i, two of the W pairs per thread
+      const int u = tid - W * W, i = u / (W / 2), l0 = (u - i * (W / 2)) * 2;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int pql = PQ[rd * 16 + l0 + e];
+        const int pql = PQ[rd * W + l0 + e];
         const int pl = pql & 0xff, ql = pql >> 8;
         const double cl = CS[2 * (l0 + e)], sl = CS[2 * (l0 + e) + 1];
         const double a = RA[i * GLD + pl], b = RA[i * GLD + ql];
@@ -477,33 +473,31 @@ jacobi_gram_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows, in
         RA[i * GLD + ql] = sl * a + cl * b;
       }
     }
-    if (rd == 3) rs[3] = clock64();
     __syncthreads();
-    if (rd == 3) rs[4] = clock64();
     double* tmp = cur;
     cur = nxt;
     nxt = tmp;
   }
   tstamp[3] = clock64();
-  // ---- apply the accumulated rotation to the staged rows, 8-row blocks per warp
+  // ---- apply the accumulated rotation to the staged rows with DMMA, 8-row blocks per warp
   const int nrb = (tot + 7) / 8;
-  for (int rb = warp; rb < nrb; rb += 16) {
+  for (int rb = warp; rb < nrb; rb += NWARP) {
     const int r0 = rb * 8;
-    double acc[4][2];
+    double acc[TG][2];
 #pragma unroll
-    for (int n = 0; n < 4; ++n) acc[n][0] = acc[n][1] = 0.0;
+    for (int n = 0; n < TG; ++n) acc[n][0] = acc[n][1] = 0.0;
 #pragma unroll
-    for (int k0 = 0; k0 < 32; k0 += 4) {
+    for (int k0 = 0; k0 < NC; k0 += 4) {
       const double a = S[(long)(k0 + t) * ld + r0 + g];
 #pragma unroll
-      for (int n = 0; n < 4; ++n) {
+      for (int n = 0; n < TG; ++n) {
         const double b = RA[(k0 + t) * GLD + n * 8 + g];
         dmma884s(acc[n][0], acc[n][1], a, b);
       }
     }
     __syncwarp();
 #pragma unroll
-    for (int n = 0; n < 4; ++n) {
+    for (int n = 0; n < TG; ++n) {
       S[(long)(n * 8 + 2 * t) * ld + r0 + g] = acc[n][0];
       S[(long)(n * 8 + 2 * t + 1) * ld + r0 + g] = acc[n][1];
     }
@@ -513,9 +507,9 @@ jacobi_gram_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows, in
   // ---- write back
   if (rc2 < tot2) {
 #pragma unroll
-    for (int it = 0; it < 16; ++it) {
-      const int k = cpar + 2 * it;
-      const int c = (k < 16) ? (c0 + k) : (c1 + k - 16);
+    for (int it = 0; it < NC / CP; ++it) {
+      const int k = cpar + CP * it;
+      const int c = (k < W) ? (c0 + k) : (c1 + k - W);
       if (c < ns) {
         const double2 v = reinterpret_cast<const double2*>(S + (long)k * ld)[rc2];
         if (rc2 < rows2)
@@ -525,11 +519,10 @@ jacobi_gram_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows, in
       }
     }
   }
-  if (tid < 16 && mo > 0.0) atomic_max_pos(info, mo);
+  if (tid < W && mo > 0.0) atomic_max_pos(info, mo);
   if (g_qr_dbg != nullptr && tid == 0 && blockIdx.x == 0) {
     tstamp[5] = clock64();
     for (int i = 0; i < 6; ++i) g_qr_dbg[2048 + i] = tstamp[i];
-    for (int i = 0; i < 5; ++i) g_qr_dbg[2056 + i] = rs[i];
   }
 }
 
@@ -1079,18 +1072,24 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
     cudaFuncSetAttribute(jacobi_diag_smem_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  // Gram-based kernel: 32 staged columns of length rows+ns plus three 32 x 36 matrices
+  // Gram-based kernel: 2W staged columns of length rows+ns plus three (2W) x 36 matrices.
+  // W = 8 by default: the round chain costs ~ W^3 per launch while a launch covers ~ W^2 pairs,
+  // and more (smaller) CTAs run concurrently.
   const int gld = ((rows + ns + 15) / 16) * 16 + 4;
-  const size_t need_gram = ((size_t)32 * gld + 3 * 32 * GLD + 32) * sizeof(double) + 31 * 16 * sizeof(unsigned short);
-  static int use_gram = -1;
+  static int use_gram = -1, gram_w = 8;
   if (use_gram < 0) {
     const char* e = getenv("TNML_SVD_GRAM");
     use_gram = e ? atoi(e) : 1;
-    cudaFuncSetAttribute(jacobi_gram_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    const char* ew = getenv("TNML_SVD_GRAM_W");
+    if (ew && atoi(ew) == 16) gram_w = 16;
     cudaFuncSetAttribute(jacobi_gram_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(jacobi_gram_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   }
-  const bool gram = use_gram && need_gram <= 220 * 1024 && ns > 16 && gld <= 512 && (rows % 2 == 0) && (ns % 2 == 0);
-  const int bw = gram ? 16 : (Wd ? Wd : JW);
+  const int GW = gram_w;
+  const size_t need_gram = ((size_t)2 * GW * gld + 3 * 2 * GW * GLD + 2 * GW) * sizeof(double) +
+                           (size_t)(2 * GW - 1) * GW * sizeof(unsigned short);
+  const bool gram = use_gram && need_gram <= 220 * 1024 && ns > GW && gld <= 512 && (rows % 2 == 0) && (ns % 2 == 0);
+  const int bw = gram ? GW : (Wd ? Wd : JW);
   const int nblk = (ns + bw - 1) / bw;
   const int nblk_e = (nblk % 2) ? nblk + 1 : nblk;
   const double conv = gram ? 0.5 : (Wd ? tol2 : tol);   // gram: 'a rotation happened' flag; smem kernels: off^2
@@ -1099,8 +1098,12 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
   for (int sw = 0; sw < max_sweeps && !hflag; ++sw) {
     if (gram) {
       for (int R = 0; R < nblk_e - 1; ++R) {
-        jacobi_gram_kernel<31><<<nblk_e / 2, 512, need_gram, st>>>(A, Jm, rows, ns, gld, nblk_e, R, tol2, w.info,
-                                                                   w.flags);
+        if (GW == 16)
+          jacobi_gram_kernel<16><<<nblk_e / 2, 512, need_gram, st>>>(A, Jm, rows, ns, gld, nblk_e, R, tol2, w.info,
+                                                                     w.flags);
+        else
+          jacobi_gram_kernel<8><<<nblk_e / 2, 256, need_gram, st>>>(A, Jm, rows, ns, gld, nblk_e, R, tol2, w.info,
+                                                                    w.flags);
         nl += 1;
       }
       jacobi_sweep_end_kernel<<<1, 32, 0, st>>>(w.info, w.flags, conv);
