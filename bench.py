@@ -267,28 +267,45 @@ def run_ours(args):
         peak, peak_src = load_peaks()
         NT = feat.shape[0]
         m = args.maxm
-        # dominant phases, from the CUDA-event breakdown
-        phases = {"proj(krgemm)": stt.ms_proj, "grad(krgram)": stt.ms_grad, "fat": stt.ms_fat,
+        # CUDA-event breakdown (events recorded on the library's own stream by tnml_set_timing)
+        phases = {"proj(krgemm)": stt.ms_proj, "grad(krgram+reduce)": stt.ms_grad, "fat": stt.ms_fat,
                   "svd": stt.ms_svd, "shift": stt.ms_shift, "other": stt.ms_other}
-        tot = sum(phases.values())
         dom = max(phases, key=phases.get)
         npass = args.npass
-        n_fwd = (2 * npass + 1) * K          # forward passes (krgemm + fat) in K bond updates
-        n_bwd = npass * K
-        # algorithmic bytes per launch (float64): fat kernel reads Q + fat env (+ writes Z on gradient passes)
+        n_fwd = (2 * npass + 1) * K          # krgemm + fat launches in K bond updates
+        n_bwd = npass * K                    # krgram launches
+        # --- dominant data-parallel kernel: krgemm<4> (FP64 tensor-core MMAs, DMMA.8x8x4)
+        # algorithmic flops per launch = 2 * NT * (4*m_l) * m_r  (8 m_l m_r per image)
+        gemm_flops_launch = 8.0 * NT * m * m
+        gemm_ms_launch = stt.ms_proj / max(1, n_fwd)
+        gemm_tf = gemm_flops_launch / (gemm_ms_launch / 1000.0) / 1e12 if gemm_ms_launch > 0 else 0.0
+        FP64_TENSOR_PEAK = 37.0   # TF/s, measured on this pool with tools/dmma_bench.cu (DMMA and DFMA share it)
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))["kernels"]["krgemm"]
+            rd = float(prof["dram__bytes_read.sum"].split()[0]) * (1e6 if "Mbyte" in prof["dram__bytes_read.sum"] else 1e3)
+            wr = float(prof["dram__bytes_write.sum"].split()[0]) * (1e6 if "Mbyte" in prof["dram__bytes_write.sum"] else 1e3)
+            traffic = (rd + wr) * (NT / 30000.0)       # captured at NT=30000 (ncu cannot replay 62 GB), linear in NT
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "kernel": "krgemm_kernel<4> (Khatri-Rao projection GEMM, FP64 mma.sync m8n8k4)",
+                "achieved": gemm_tf, "peak": FP64_TENSOR_PEAK, "unit": "TFLOP/s", "frac": gemm_tf / FP64_TENSOR_PEAK,
+                "traffic": traffic,
+                "peak_source": "FP64 tensor/FMA pipe measured with tools/dmma_bench.cu on this pool's B200 (37.0 TF/s); "
+                               "MEASURED_PEAKS.json holds bf16 and HBM only -- the path computes in f64 (DESIGN.md 3)",
+                "launch_avg_ms": gemm_ms_launch, "launches_in_region": n_fwd,
+                "algorithmic_flops_per_launch": gemm_flops_launch,
+                "phase_ms_per_step": {k: v / K for k, v in phases.items()}, "dominant_phase": dom}
+        # --- the HBM-bound kernel of the path: fat_kernel_t (label-carrying environment stream)
         fat_bytes = 8.0 * NT * (m + 10 * m + 1) * n_fwd + 8.0 * NT * m * n_bwd
         fat_gbs = fat_bytes / (stt.ms_fat / 1000.0) / 1e9 if stt.ms_fat > 0 else 0.0
-        gemm_flops = 8.0 * NT * m * m * (n_fwd + n_bwd)
-        gemm_tf = gemm_flops / ((stt.ms_proj + stt.ms_grad) / 1000.0) / 1e12 if stt.ms_proj > 0 else 0.0
-        roof = {"bound": "hbm", "kernel": "fat_kernel_t (label-carrying environment stream)",
-                "achieved": fat_gbs, "peak": peak, "unit": "GB/s", "frac": fat_gbs / peak, "traffic": None,
-                "peak_source": peak_src,
-                "launch_avg_ms": stt.ms_fat / max(1, n_fwd),
-                "phase_ms_per_step": {k: v / K for k, v in phases.items()}, "dominant_phase": dom,
-                "fp64_gemm": {"achieved_tflops": gemm_tf, "peak_tflops_nominal": 40.0,
-                              "frac": gemm_tf / 40.0,
-                              "note": "krgemm/krgram are FP64-FMA bound (no FP64 tcgen05 kind exists); "
-                                      "MEASURED_PEAKS.json has no FP64 figure, nominal B200 FP64 = 40 TF/s"}}
+        roof_hbm = {"bound": "hbm", "kernel": "fat_kernel_t", "achieved": fat_gbs, "peak": peak, "unit": "GB/s",
+                    "frac": fat_gbs / peak, "peak_source": peak_src, "launch_avg_ms": stt.ms_fat / max(1, n_fwd),
+                    "algorithmic_bytes_per_launch": 8.0 * NT * (11 * m + 1)}
+        # --- the serial term: truncated SVD of the 2m x 2m bond matrix (replicated on every rank)
+        svd_info = {"ms_per_step": stt.ms_svd / K, "sweeps": [int(r.svd_sweeps) for r in res_t][:8],
+                    "note": "Householder QR + Gram-based block Jacobi (latency bound, ~15 CTAs); largest summed "
+                            "share of the step, see profiles/r01_ncu_summary.md"}
         line = {"metric": "bond-updates/sec", "value": value, "unit": "bond-updates/sec", "n_gpus": world,
                 "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, world),
@@ -297,9 +314,9 @@ def run_ours(args):
                         "d2h_bytes_per_step": d2h / K,
                         "note": "host-resident MPS: W(b),W(b+1) H2D before and D2H after every bond update "
                                 "through the C-ABI; images/environments are resident state (TrainStates)"},
-                "gpu_launches": int(st.launches), "clocks": clocks, "roofline": roof,
+                "gpu_launches": int(st.launches), "clocks": clocks, "roofline": roof, "roofline_hbm": roof_hbm,
+                "svd": svd_info,
                 "setup_s": setup_s, "newm": [int(r.newm) for r in res][:8],
-                "svd_sweeps": [int(r.svd_sweeps) for r in res][:8],
                 "cost_per_image": [r.cost / NTg for r in res][:4]}
         if not args.no_cpu_baseline:
             base, _ = cpu_baseline(args, steps=1)
