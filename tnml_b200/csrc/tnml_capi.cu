@@ -548,6 +548,7 @@ int tnml_destroy(tnml_handle h) {
                   h->svd.M, h->svd.tau, h->svd.ready, h->svd.Y};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  if (h->svd.gexec) cudaGraphExecDestroy(h->svd.gexec);
   if (h->hpin) cudaFreeHost(h->hpin);
   for (auto& e : h->evs) {
     cudaEventDestroy(e.a);

@@ -84,6 +84,8 @@ struct SvdWork {
   double* Y = nullptr;     // [kept][nb] big-side unit vectors
   long capM = 0, capY = 0;
   int use_qr = -1;         // -1 auto, 0 never, 1 always (TNML_SVD_QR)
+  cudaGraphExec_t gexec = nullptr;   // one Jacobi sweep, captured for the current (buffers, dims)
+  long gkey[6] = {0, 0, 0, 0, 0, 0};
 };
 // Gather canonical B into X (tall orientation), run block one-sided Jacobi,
 // sort, apply ITensor's truncation rule, scatter U -> W(c), S*V -> W(c+dc).

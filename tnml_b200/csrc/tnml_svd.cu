@@ -1097,18 +1097,47 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
   int hflag = 0;
   for (int sw = 0; sw < max_sweeps && !hflag; ++sw) {
     if (gram) {
-      for (int R = 0; R < nblk_e - 1; ++R) {
-        if (GW == 16)
-          jacobi_gram_kernel<16><<<nblk_e / 2, 512, need_gram, st>>>(A, Jm, rows, ns, gld, nblk_e, R, tol2, w.info,
-                                                                     w.flags);
-        else
-          jacobi_gram_kernel<8><<<nblk_e / 2, 256, need_gram, st>>>(A, Jm, rows, ns, gld, nblk_e, R, tol2, w.info,
-                                                                    w.flags);
-        nl += 1;
+      // one sweep = nblk_e-1 launches + bookkeeping; replayed as a CUDA graph (the launch gaps of
+      // ~300 back-to-back 10 us kernels were ~0.8 ms per SVD)
+      cudaGraphExec_t& gexec = w.gexec;
+      long* gkey = w.gkey;
+      const long key[6] = {(long)(size_t)A, (long)(size_t)Jm, rows, ns, GW, (long)(size_t)w.info};
+      bool same = gexec != nullptr;
+      for (int i = 0; i < 6; ++i) same = same && (gkey[i] == key[i]);
+      static int use_graph = -1;
+      if (use_graph < 0) use_graph = getenv("TNML_SVD_NOGRAPH") ? 0 : 1;
+      auto enqueue = [&]() {
+        for (int R = 0; R < nblk_e - 1; ++R) {
+          if (GW == 16)
+            jacobi_gram_kernel<16><<<nblk_e / 2, 512, need_gram, st>>>(A, Jm, rows, ns, gld, nblk_e, R, tol2, w.info,
+                                                                       w.flags);
+          else
+            jacobi_gram_kernel<8><<<nblk_e / 2, 256, need_gram, st>>>(A, Jm, rows, ns, gld, nblk_e, R, tol2, w.info,
+                                                                      w.flags);
+        }
+        jacobi_sweep_end_kernel<<<1, 32, 0, st>>>(w.info, w.flags, conv);
+      };
+      if (use_graph) {
+        if (!same) {
+          if (gexec) cudaGraphExecDestroy(gexec);
+          gexec = nullptr;
+          cudaGraph_t graph;
+          if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            enqueue();
+            if (cudaStreamEndCapture(st, &graph) == cudaSuccess && graph) {
+              if (cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) gexec = nullptr;
+              cudaGraphDestroy(graph);
+            }
+          }
+          for (int i = 0; i < 6; ++i) gkey[i] = gexec ? key[i] : 0;
+        }
+        if (gexec && cudaGraphLaunch(gexec, st) != cudaSuccess) return -2;
+        if (!gexec) enqueue();
+      } else {
+        enqueue();
       }
-      jacobi_sweep_end_kernel<<<1, 32, 0, st>>>(w.info, w.flags, conv);
-      nl += 1;
-      if (sw >= 2) {
+      nl += nblk_e;
+      if (sw >= 6) {
         if (cudaMemcpyAsync(&hflag, w.flags, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
         if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
       }
