@@ -36,6 +36,9 @@ def parse():
     ap.add_argument("--first-bond", type=int, default=10)
     ap.add_argument("--cpu-sample", type=int, default=1024, help="images in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cg-reuse-forward", type=int, default=0,
+                    help="1: linear update of the forward outputs between CG passes (tnml_set_option); "
+                         "0 (default): literal recompute like fixedL.cc:412-421")
     return ap.parse_args()
 
 
@@ -139,7 +142,7 @@ def config_dict(args, world):
     return {"workload": "BASELINE config 3/4: synthetic 14x14 MNIST-shaped, N=196 sites d=2 NL=10, "
                         f"NT={args.nt} images total, maxm={args.maxm} minm={max(10, args.maxm // 2)} "
                         f"Npass={args.npass} cutoff=1e-10, bonds {args.first_bond}.. (class L, ml=mr={args.maxm})",
-            "NT_total": args.nt, "N": 196, "maxm": args.maxm, "Npass": args.npass,
+            "NT_total": args.nt, "N": 196, "maxm": args.maxm, "Npass": args.npass, "cg_reuse_forward": int(getattr(args, "cg_reuse_forward", 0)),
             "parallelism": f"dp{world} (images sharded, NCCL all-reduce of the bond gradient)" if world > 1 else "dp1",
             "l2": "per-bond inputs (environment cache, >=600 MB/rank at NT=60000) exceed the 126 MB L2; no flush needed"}
 
@@ -186,6 +189,7 @@ def run_ours(args):
             uid = torch.tensor(list(capi.comm_get_unique_id()), dtype=torch.uint8, device="cuda")
         dist.broadcast(uid, 0)
         h.comm_init_rank(world, rank, bytes(uid.cpu().tolist()))
+    h.set_option("cg_reuse_forward", args.cg_reuse_forward)
     h.init_envs()
     b0 = args.first_bond
     for bb in range(1, b0):                     # left envs up to the first timed bond
@@ -263,6 +267,13 @@ def run_ours(args):
     ms_e, res_e, h2d, d2h = timed(K, b, e2e=True)
     e2e_value = K / (ms_e / 1000.0)
 
+    value_reuse = None
+    if not args.cg_reuse_forward and b + K + 2 < 96:
+        h.set_option("cg_reuse_forward", 1)
+        ms_r, _, _, _ = timed(K, b + K)
+        h.set_option("cg_reuse_forward", 0)
+        value_reuse = K / (ms_r / 1000.0)
+
     if rank == 0:
         peak, peak_src = load_peaks()
         NT = feat.shape[0]
@@ -272,12 +283,14 @@ def run_ours(args):
                   "svd": stt.ms_svd, "shift": stt.ms_shift, "other": stt.ms_other}
         dom = max(phases, key=phases.get)
         npass = args.npass
-        n_fwd = (2 * npass + 1) * K          # krgemm + fat launches in K bond updates
+        reuse = int(args.cg_reuse_forward)
+        n_gemm = ((npass + 2) if reuse else (2 * npass + 1)) * K   # krgemm launches in K bond updates
+        n_fwd = (2 * npass + 1) * K          # fat-kernel launches (passes over the fat environment)
         n_bwd = npass * K                    # krgram launches
         # --- dominant data-parallel kernel: krgemm<4> (FP64 tensor-core MMAs, DMMA.8x8x4)
         # algorithmic flops per launch = 2 * NT * (4*m_l) * m_r  (8 m_l m_r per image)
         gemm_flops_launch = 8.0 * NT * m * m
-        gemm_ms_launch = stt.ms_proj / max(1, n_fwd)
+        gemm_ms_launch = stt.ms_proj / max(1, n_gemm)
         gemm_tf = gemm_flops_launch / (gemm_ms_launch / 1000.0) / 1e12 if gemm_ms_launch > 0 else 0.0
         FP64_TENSOR_PEAK = 37.0   # TF/s, measured on this pool with tools/dmma_bench.cu (DMMA and DFMA share it)
         traffic = None
@@ -293,7 +306,7 @@ def run_ours(args):
                 "traffic": traffic,
                 "peak_source": "FP64 tensor/FMA pipe measured with tools/dmma_bench.cu on this pool's B200 (37.0 TF/s); "
                                "MEASURED_PEAKS.json holds bf16 and HBM only -- the path computes in f64 (DESIGN.md 3)",
-                "launch_avg_ms": gemm_ms_launch, "launches_in_region": n_fwd,
+                "launch_avg_ms": gemm_ms_launch, "launches_in_region": n_gemm,
                 "algorithmic_flops_per_launch": gemm_flops_launch,
                 "phase_ms_per_step": {k: v / K for k, v in phases.items()}, "dominant_phase": dom}
         # --- the HBM-bound kernel of the path: fat_kernel_t (label-carrying environment stream)
@@ -316,6 +329,7 @@ def run_ours(args):
                                 "through the C-ABI; images/environments are resident state (TrainStates)"},
                 "gpu_launches": int(st.launches), "clocks": clocks, "roofline": roof, "roofline_hbm": roof_hbm,
                 "svd": svd_info,
+                "value_cg_reuse_forward": value_reuse,
                 "setup_s": setup_s, "newm": [int(r.newm) for r in res][:8],
                 "cost_per_image": [r.cost / NTg for r in res][:4]}
         if not args.no_cpu_baseline:

@@ -298,3 +298,32 @@ def test_svd_qr_preconditioned_path(capi, b, ha):
             h.set_site(b, W[b])
             h.set_site(b + 1, W[b + 1])
     h.close()
+
+
+@pytest.mark.parametrize("b", [3, 4, 7])
+def test_cg_reuse_forward_option(capi, b):
+    """cg_reuse_forward=1 (linear update of the forward outputs) is the same mathematics as the
+    literal recompute; results agree to the CG's own noise amplification (classes L, C, R)."""
+    feat, labels, W = make_problem(N=10, NT=700, m0=4)
+    ts = O.TrainStates(feat, labels)
+    ts.init(W)
+    h = _gpu_state(capi, feat, labels, W)
+    _walk_both(h, ts, W, capi, b)
+    B = O.form_bond(W[b], W[b + 1])
+    Bo, costs_o, _ = O.cgrad(B, ts, 4)
+    h.set_option("cg_reuse_forward", 0)
+    h.bond_load(B)
+    c0, _ = h.cgrad(4)
+    B0 = h.bond_store()
+    h.set_option("cg_reuse_forward", 1)
+    h.bond_load(B)
+    c1, _ = h.cgrad(4)
+    B1 = h.bond_store()
+    # class C (b=4) at this size is ill-conditioned: the third pass already amplifies 1e-16
+    # differences to ~1e-6 (same effect between two float64 oracle orderings)
+    tol = 1e-4 if b == 4 else 1e-10
+    assert rel(c1[:2], c0[:2]) < 1e-10 and rel(c1, c0) < tol and rel(c1, costs_o) < max(tol, 1e-9)
+    assert rel(B1, B0) < (1e-2 if b == 4 else 1e-6)
+    with pytest.raises(capi.TnmlError):
+        h.set_option("no_such_option", 1)
+    h.close()

@@ -54,7 +54,7 @@ SYMBOLS = [
     "tnml_set_site", "tnml_get_site_dims", "tnml_get_site", "tnml_init_envs", "tnml_set_bond",
     "tnml_bond_form", "tnml_bond_dims", "tnml_bond_load", "tnml_bond_store", "tnml_cgrad",
     "tnml_svd_split", "tnml_quadcost", "tnml_shift_env", "tnml_bond_update", "tnml_predict",
-    "tnml_get_env", "tnml_comm_get_unique_id", "tnml_comm_init_rank", "tnml_get_stats",
+    "tnml_get_env", "tnml_comm_get_unique_id", "tnml_comm_init_rank", "tnml_set_option", "tnml_get_stats",
     "tnml_set_timing", "tnml_synchronize", "tnml_stream",
 ]
 
@@ -96,6 +96,7 @@ def load_library():
     lib.tnml_get_env.argtypes = [vp, i, ip, ip, vp, C.c_size_t]
     lib.tnml_comm_get_unique_id.argtypes = [vp]
     lib.tnml_comm_init_rank.argtypes = [vp, i, i, vp]
+    lib.tnml_set_option.argtypes = [vp, C.c_char_p, d]
     lib.tnml_get_stats.argtypes = [vp, C.POINTER(Stats), i]
     lib.tnml_set_timing.argtypes = [vp, i]
     lib.tnml_synchronize.argtypes = [vp]
@@ -238,6 +239,9 @@ class Handle:
     def comm_init_rank(self, nranks, rank, uid: bytes):
         buf = (C.c_uint8 * UNIQUE_ID_BYTES).from_buffer_copy(uid)
         self._ck(self.lib.tnml_comm_init_rank(self._h, nranks, rank, buf))
+
+    def set_option(self, name: str, value: float):
+        self._ck(self.lib.tnml_set_option(self._h, name.encode(), float(value)))
 
     def stats(self, reset=False) -> Stats:
         s = Stats()

@@ -109,6 +109,8 @@ struct tnml_handle_s {
   bool bond_valid = false;
   DBuf B, r, p, G, T, Gpart, Q, Z, Bm;
   double* P = nullptr;  // [NT][NL]
+  double* PV = nullptr; // [NT][NL]  p*v_n of the current CG pass (cg_reuse_forward)
+  int cg_reuse_forward = 0;
   int32_t* pred = nullptr;
   double* stats_partial = nullptr;
   int nfat_blocks = 0;
@@ -285,7 +287,8 @@ int setup_geom(tnml_handle h, int b) {
 
 // forward pass: P[n][l] for bond-shaped tensor X (canonical layout).
 // mode: FAT_GRAD (also produces Z), FAT_PAP, FAT_COST.  Leaves stats in dstats.
-int forward(tnml_handle h, const double* X, int mode, double* dstats) {
+int forward(tnml_handle h, const double* X, int mode, double* dstats, double* Pout = nullptr) {
+  if (!Pout) Pout = h->P;
   const int b = h->currb;
   const BondGeom& g = h->g;
   EnvRef le, re;
@@ -308,7 +311,7 @@ int forward(tnml_handle h, const double* X, int mode, double* dstats) {
     }
     {
       PhaseTimer t(h, PH_FAT);
-      fat_kernel(h->st, mode, h->Q.p, fat.p, mf, h->labels, h->P, h->Z.p, h->pred, h->stats_partial,
+      fat_kernel(h->st, mode, h->Q.p, fat.p, mf, h->labels, Pout, h->Z.p, h->pred, h->stats_partial,
                  h->nfat_blocks, NT);
       CKL();
       reduce_stats(h->st, h->stats_partial, h->nfat_blocks, dstats);
@@ -328,7 +331,7 @@ int forward(tnml_handle h, const double* X, int mode, double* dstats) {
     }
     {
       PhaseTimer t(h, PH_FAT);
-      fat_kernel(h->st, mode == FAT_GRAD ? FAT_GRAD_OUTER : mode, re.p, h->Q.p, g.mr, h->labels, h->P, h->Z.p,
+      fat_kernel(h->st, mode == FAT_GRAD ? FAT_GRAD_OUTER : mode, re.p, h->Q.p, g.mr, h->labels, Pout, h->Z.p,
                  h->pred, h->stats_partial, h->nfat_blocks, NT);
       CKL();
       reduce_stats(h->st, h->stats_partial, h->nfat_blocks, dstats);
@@ -396,6 +399,44 @@ int grad_eval(tnml_handle h, const double* X, double* hstats) {
   const long n = h->g.size();
   TRY(ensure(h, h->G, (size_t)n + 16));
   TRY(forward(h, X, FAT_GRAD, h->dscal));
+  TRY(backward(h));
+  CK(cudaMemcpyAsync(h->G.p + n, h->dscal, 16 * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  TRY(allreduce(h, h->G.p, (size_t)n + 16));
+  TRY(fetch(h, h->G.p + n, 16, hstats));
+  return 0;
+}
+
+// cg_reuse_forward: the forward outputs are linear in the bond tensor, P(B + a p) = P(B) + a P(p),
+// and P(p) was just computed for pAp -- so the next residual needs only the backward half:
+// dP = delta - P, cost statistics, Z (one pass over the fat environment) and the krgram contraction.
+int grad_from_P(tnml_handle h, double* hstats) {
+  const int b = h->currb;
+  const BondGeom& g = h->g;
+  EnvRef le, re;
+  TRY(left_env(h, b, le));
+  TRY(right_env(h, b, re));
+  const long NT = h->NT;
+  const long n = g.size();
+  TRY(ensure(h, h->G, (size_t)n + 16));
+  {
+    PhaseTimer t(h, PH_FAT);
+    if (h->cls != 1) {
+      const EnvRef& fat = (h->cls == 0) ? re : le;
+      TRY(ensure(h, h->Z, (size_t)NT * fat.m));
+      fat_kernel(h->st, FAT_BWD, h->Q.p, fat.p, fat.m, h->labels, h->P, h->Z.p, h->pred, h->stats_partial,
+                 h->nfat_blocks, NT);
+      h->stats.alg_bytes += 8.0 * NT * ((double)NL * fat.m + fat.m + NL);
+      h->stats.alg_flops += (double)NT * 2.0 * NL * fat.m;
+    } else {
+      TRY(ensure(h, h->Z, (size_t)NT * NL * g.mr));
+      fat_kernel(h->st, FAT_BWD_OUTER, re.p, h->Q.p, g.mr, h->labels, h->P, h->Z.p, h->pred, h->stats_partial,
+                 h->nfat_blocks, NT);
+    }
+    CKL();
+    reduce_stats(h->st, h->stats_partial, h->nfat_blocks, h->dscal);
+    CKL();
+    h->stats.launches += 2;
+  }
   TRY(backward(h));
   CK(cudaMemcpyAsync(h->G.p + n, h->dscal, 16 * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
   TRY(allreduce(h, h->G.p, (size_t)n + 16));
@@ -543,7 +584,7 @@ int tnml_destroy(tnml_handle h) {
   DBuf* bufs[] = {&h->B, &h->r, &h->p, &h->G, &h->T, &h->Gpart, &h->Q, &h->Z, &h->Bm};
   for (DBuf* b : bufs)
     if (b->p) cudaFree(b->p);
-  void* ptrs[] = {h->feat, h->labels, h->ones, h->P, h->pred, h->stats_partial, h->dscal, h->dot_scratch,
+  void* ptrs[] = {h->feat, h->labels, h->ones, h->P, h->PV, h->pred, h->stats_partial, h->dscal, h->dot_scratch,
                   h->svd.X, h->svd.J, h->svd.sig2, h->svd.perm, h->svd.info, h->svd.flags,
                   h->svd.M, h->svd.tau, h->svd.ready, h->svd.Y};
   for (void* p : ptrs)
@@ -572,10 +613,10 @@ int tnml_set_images(tnml_handle h, int64_t NT, int N, const double* feat, const 
     if (s.p) cudaFree(s.p);
   for (auto& s : h->W)
     if (s.d) cudaFree(s.d);
-  void* ptrs[] = {h->feat, h->labels, h->ones, h->P, h->pred};
+  void* ptrs[] = {h->feat, h->labels, h->ones, h->P, h->PV, h->pred};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  h->feat = nullptr, h->labels = nullptr, h->ones = nullptr, h->P = nullptr, h->pred = nullptr;
+  h->feat = nullptr, h->labels = nullptr, h->ones = nullptr, h->P = nullptr, h->PV = nullptr, h->pred = nullptr;
   h->NT = NT;
   h->NTg = NT_global > 0 ? NT_global : NT;
   h->first = first;
@@ -590,6 +631,7 @@ int tnml_set_images(tnml_handle h, int64_t NT, int N, const double* feat, const 
   CK(cudaMalloc(&h->labels, NT * sizeof(int32_t)));
   CK(cudaMalloc(&h->ones, NT * sizeof(double)));
   CK(cudaMalloc(&h->P, (size_t)NT * NL * sizeof(double)));
+  CK(cudaMalloc(&h->PV, (size_t)NT * NL * sizeof(double)));
   CK(cudaMalloc(&h->pred, NT * sizeof(int32_t)));
   // [NT][N][2] -> [N+2][NT][2] (site-major: one bond's features are contiguous)
   std::vector<double> stage(nf, 0.0);
@@ -735,7 +777,7 @@ int tnml_cgrad(tnml_handle h, int Npass, double lambda, double cconv, double* co
   TRY(ddot(h, n, h->r.p, h->r.p, &rr));
   for (int pass = 1; pass <= Npass; ++pass) {
     // pAp = sum_n |p v_n|^2 + lambda |p|^2          (393-403)
-    TRY(forward(h, h->p.p, FAT_PAP, h->dscal));
+    TRY(forward(h, h->p.p, FAT_PAP, h->dscal, h->cg_reuse_forward ? h->PV : nullptr));
     TRY(allreduce(h, h->dscal, 16));
     TRY(fetch(h, h->dscal, 16, hs));
     double pAp = hs[11];
@@ -749,7 +791,14 @@ int tnml_cgrad(tnml_handle h, int Npass, double lambda, double cconv, double* co
     CKL();
     h->stats.launches += 1;
     if (pass == Npass) break;                         // 409
-    TRY(grad_eval(h, h->B.p, hs));                    // 412-421
+    if (h->cg_reuse_forward) {
+      axpby(h->st, (long)h->NT * NL, a, h->PV, 1.0, h->P);   // P(B + a p) = P(B) + a P(p)
+      CKL();
+      h->stats.launches += 1;
+      TRY(grad_from_P(h, hs));
+    } else {
+      TRY(grad_eval(h, h->B.p, hs));                  // 412-421
+    }
     if (lambda != 0.0) {
       axpby(h->st, n, -lambda, h->B.p, 1.0, h->G.p);  // 422
       CKL();
@@ -937,6 +986,15 @@ int tnml_comm_init_rank(tnml_handle h, int nranks, int rank, const uint8_t* id) 
   h->nranks = nranks;
   h->rank = rank;
   return TNML_OK;
+}
+
+int tnml_set_option(tnml_handle h, const char* name, double value) {
+  if (!h || !name) return TNML_ERR_INVALID;
+  if (strcmp(name, "cg_reuse_forward") == 0) {
+    h->cg_reuse_forward = (value != 0.0);
+    return TNML_OK;
+  }
+  return fail(h, TNML_ERR_INVALID, "unknown option %s", name);
 }
 
 int tnml_get_stats(tnml_handle h, tnml_stats* out, int reset) {

@@ -356,6 +356,9 @@ fat_kernel_t(const double* __restrict__ Q, const double* __restrict__ F, int m,
 #pragma unroll
     for (int l = 0; l < NL; ++l) pl[l] = 0.0;
     constexpr int C = (MCH > 0) ? MCH : 1;
+    constexpr bool GIVEN_P = (MODE == FAT_BWD || MODE == FAT_BWD_OUTER);
+    constexpr bool DO_Z = (MODE == FAT_GRAD || MODE == FAT_BWD);
+    constexpr bool DO_ZOUTER = (MODE == FAT_GRAD_OUTER || MODE == FAT_BWD_OUTER);
     double qv[C];
     double fv[NL][C];
     if (MCH > 0) {
@@ -363,27 +366,34 @@ fat_kernel_t(const double* __restrict__ Q, const double* __restrict__ F, int m,
       for (int c = 0; c < C; ++c) {
         const int f = lane + 32 * c;
         const bool ok = f < m;
-        qv[c] = ok ? q[f] : 0.0;
+        qv[c] = (ok && !(GIVEN_P && DO_Z)) ? q[f] : 0.0;            // FAT_BWD needs no Q
 #pragma unroll
-        for (int l = 0; l < NL; ++l) fv[l][c] = ok ? Fn[(long)l * m + f] : 0.0;
+        for (int l = 0; l < NL; ++l) fv[l][c] = (ok && !(GIVEN_P && DO_ZOUTER)) ? Fn[(long)l * m + f] : 0.0;
       }
+      if (!GIVEN_P) {
 #pragma unroll
-      for (int c = 0; c < C; ++c)
+        for (int c = 0; c < C; ++c)
 #pragma unroll
-        for (int l = 0; l < NL; ++l) pl[l] = fma(qv[c], fv[l][c], pl[l]);
-    } else {
+          for (int l = 0; l < NL; ++l) pl[l] = fma(qv[c], fv[l][c], pl[l]);
+      }
+    } else if (!GIVEN_P) {
       for (int f = lane; f < m; f += 32) {
         double x = q[f];
 #pragma unroll
         for (int l = 0; l < NL; ++l) pl[l] = fma(x, Fn[(long)l * m + f], pl[l]);
       }
     }
+    if (GIVEN_P) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+      for (int l = 0; l < NL; ++l) pl[l] = P[n * NL + l];
+    } else {
 #pragma unroll
-      for (int l = 0; l < NL; ++l) pl[l] += __shfl_xor_sync(0xffffffffu, pl[l], o);
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int l = 0; l < NL; ++l) pl[l] += __shfl_xor_sync(0xffffffffu, pl[l], o);
+      }
     }
-    if (P != nullptr) {
+    if (P != nullptr && !GIVEN_P) {
       double mine = 0.0;
 #pragma unroll
       for (int l = 0; l < NL; ++l) mine = (lane == l) ? pl[l] : mine;
@@ -415,7 +425,7 @@ fat_kernel_t(const double* __restrict__ Q, const double* __restrict__ F, int m,
       }
 #pragma unroll
       for (int l = 0; l < NL; ++l) cst[l] += (l == lab) ? e : 0.0;
-      if (MODE == FAT_GRAD) {
+      if (DO_Z) {
         double* z = Z + n * m;
         if (MCH > 0) {
 #pragma unroll
@@ -434,7 +444,7 @@ fat_kernel_t(const double* __restrict__ Q, const double* __restrict__ F, int m,
             z[f] = sacc;
           }
         }
-      } else if (MODE == FAT_GRAD_OUTER) {
+      } else if (DO_ZOUTER) {
         double* z = Z + n * (long)NL * m;
         if (MCH > 0) {
 #pragma unroll
@@ -500,6 +510,12 @@ void fat_kernel(cudaStream_t st, int mode, const double* Q, const double* F, int
       break;
     case FAT_COST:
       fat_launch<FAT_COST>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
+      break;
+    case FAT_BWD:
+      fat_launch<FAT_BWD>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
+      break;
+    case FAT_BWD_OUTER:
+      fat_launch<FAT_BWD_OUTER>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
       break;
     default:
       fat_launch<FAT_GRAD_OUTER>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);

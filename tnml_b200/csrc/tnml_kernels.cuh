@@ -35,6 +35,8 @@ enum FatMode : int {
   FAT_PAP = 1,    // stats[11] += sum_l P[l]^2
   FAT_COST = 2,   // stats (cost per label, ncorrect), pred
   FAT_GRAD_OUTER = 3,  // class C: Zfat[n][l][f] = dP[l]*Q[n][f]
+  FAT_BWD = 4,         // P[n][l] is given (linear update of the forward outputs): stats + Z only
+  FAT_BWD_OUTER = 5,   // class C variant of FAT_BWD
 };
 // stats layout (double[16]): [0..9] cost per label, [10] ncorrect, [11] sum |P|^2
 void fat_kernel(cudaStream_t st, int mode, const double* Q, const double* F, int m, const int32_t* labels,
