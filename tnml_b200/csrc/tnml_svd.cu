@@ -374,8 +374,9 @@ jacobi_gram_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows, in
   double* G0 = sm + (long)NC * ld;      // [NC][GLD]
   double* G1 = G0 + NC * GLD;
   double* RA = G1 + NC * GLD;
-  double* CS = RA + NC * GLD;                                        // [W][2]
-  unsigned short* PQ = reinterpret_cast<unsigned short*>(CS + 2 * W);   // [NR][W]  p | q << 8
+  double* CS = RA + NC * GLD;                                        // [2][W][2] (double buffered)
+  unsigned short* PQ = reinterpret_cast<unsigned short*>(CS + 4 * W);   // [NR][W]  p | q << 8
+  unsigned char* POS = reinterpret_cast<unsigned char*>(PQ + NR * W);    // [NR][NC] pair*2 + (0 first, 1 second)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   int P, Q;
   rr_pair(nblk_e, R, blockIdx.x, P, Q);
@@ -411,6 +412,8 @@ jacobi_gram_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows, in
     int p, q;
     rr_pair(NC, rd, k, p, q);
     PQ[i] = (unsigned short)(p | (q << 8));
+    POS[rd * NC + p] = (unsigned char)(2 * k);
+    POS[rd * NC + q] = (unsigned char)(2 * k + 1);
   }
   __syncthreads();
   tstamp[1] = clock64();
@@ -431,27 +434,35 @@ jacobi_gram_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows, in
   }
   __syncthreads();
   tstamp[2] = clock64();
-  // ---- rotation rounds on the Gram matrix: each rotation is computed once (W threads), then
-  //      W*W threads update one 2x2 block of G each (ping-pong) and NC*W/2 threads update RA
+  // ---- rotation rounds on the Gram matrix.  Per round: W*W threads update one 2x2 block of
+  //      G each (ping-pong), NC*W/2 threads update RA, and W "look-ahead" threads compute the
+  //      rotations of the NEXT round from privately recomputed entries of the updated G, so that
+  //      the serial chain (load -> two rsqrt -> store) overlaps the updates: one barrier per round.
   double* cur = G0;
   double* nxt = G1;
   double mo = 0.0;
+  if (tid < W) {   // rotations of round 0
+    const int pq = PQ[tid];
+    const int p = pq & 0xff, q = pq >> 8;
+    double c, sn, rot;
+    plane_rot(cur[p * GLD + p], cur[q * GLD + q], cur[p * GLD + q], tol2, c, sn, rot);
+    CS[2 * tid] = c;
+    CS[2 * tid + 1] = sn;
+    mo = fmax(mo, rot);
+  }
+  __syncthreads();
+  constexpr int RE = (W == 16) ? 4 : 2;          // pairs per RA-update thread
+  constexpr int T_BLK = W * W, T_RA = NC * W / RE;
+  static_assert(T_BLK + T_RA + W <= NTH, "thread budget");
   for (int rd = 0; rd < NR; ++rd) {
-    if (tid < W) {
-      const int pq = PQ[rd * W + tid];
-      const int p = pq & 0xff, q = pq >> 8;
-      double c, sn, rot;
-      plane_rot(cur[p * GLD + p], cur[q * GLD + q], cur[p * GLD + q], tol2, c, sn, rot);
-      CS[2 * tid] = c;
-      CS[2 * tid + 1] = sn;
-      mo = fmax(mo, rot);
-    }
-    __syncthreads();
-    if (tid < W * W) {
+    const double* cs = CS + (rd & 1) * 2 * W;
+    double* csn = CS + ((rd + 1) & 1) * 2 * W;
+    const unsigned short* pqr = PQ + rd * W;
+    if (tid < T_BLK) {
       const int k = tid / W, l = tid - k * W;
-      const int pqk = PQ[rd * W + k], pql = PQ[rd * W + l];
+      const int pqk = pqr[k], pql = pqr[l];
       const int pk = pqk & 0xff, qk = pqk >> 8, pl = pql & 0xff, ql = pql >> 8;
-      const double ck = CS[2 * k], sk = CS[2 * k + 1], cl = CS[2 * l], sl = CS[2 * l + 1];
+      const double ck = cs[2 * k], sk = cs[2 * k + 1], cl = cs[2 * l], sl = cs[2 * l + 1];
       const double g00 = cur[pk * GLD + pl], g01 = cur[pk * GLD + ql];
       const double g10 = cur[qk * GLD + pl], g11 = cur[qk * GLD + ql];
       // T = R_k^T * Gb ; Gb' = T * R_l   with R = [[c, s], [-s, c]]
@@ -461,17 +472,43 @@ jacobi_gram_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows, in
       nxt[pk * GLD + ql] = t00 * sl + t01 * cl;
       nxt[qk * GLD + pl] = t10 * cl - t11 * sl;
       nxt[qk * GLD + ql] = t10 * sl + t11 * cl;
-    } else if (tid < W * W + NC * W / 2) {   // RA <- RA * R : row i, two of the W pairs per thread
-      const int u = tid - W * W, i = u / (W / 2), l0 = (u - i * (W / 2)) * 2;
+    } else if (tid < T_BLK + T_RA) {   // RA <- RA * R : row i, two of the W pairs per thread
+      const int u = tid - T_BLK, i = u / (W / RE), l0 = (u - i * (W / RE)) * RE;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int pql = PQ[rd * W + l0 + e];
+      for (int e = 0; e < RE; ++e) {
+        const int pql = pqr[l0 + e];
         const int pl = pql & 0xff, ql = pql >> 8;
-        const double cl = CS[2 * (l0 + e)], sl = CS[2 * (l0 + e) + 1];
+        const double cl = cs[2 * (l0 + e)], sl = cs[2 * (l0 + e) + 1];
         const double a = RA[i * GLD + pl], b = RA[i * GLD + ql];
         RA[i * GLD + pl] = cl * a - sl * b;
         RA[i * GLD + ql] = sl * a + cl * b;
       }
+    } else if (tid >= NTH - W && rd + 1 < NR) {   // look-ahead: pair j of round rd+1
+      const int j = tid - (NTH - W);
+      const int pqn = PQ[(rd + 1) * W + j];
+      const int x = pqn & 0xff, y = pqn >> 8;
+      // position of x, y in THIS round's pairing: partner and rotation column
+      const int ix = POS[rd * NC + x], iy = POS[rd * NC + y];
+      const int kx = ix >> 1, ky = iy >> 1;
+      const int pqx = pqr[kx], pqy = pqr[ky];
+      const int xp = pqx & 0xff, xq = pqx >> 8, yp = pqy & 0xff, yq = pqy >> 8;
+      // column of R that produces the new vector: first of pair -> (c, -s), second -> (s, c)
+      const double cx = cs[2 * kx], sx = cs[2 * kx + 1], cy = cs[2 * ky], sy = cs[2 * ky + 1];
+      const double ux = (ix & 1) ? sx : cx, vx = (ix & 1) ? cx : -sx;   // new_x = ux*old[xp] + vx*old[xq]
+      const double uy = (iy & 1) ? sy : cy, vy = (iy & 1) ? cy : -sy;
+      auto quad = [&](int ap, int aq, double ua, double va, int bp, int bq, double ub, double vb) {
+        const double g00 = cur[ap * GLD + bp], g01 = cur[ap * GLD + bq];
+        const double g10 = cur[aq * GLD + bp], g11 = cur[aq * GLD + bq];
+        return ua * (g00 * ub + g01 * vb) + va * (g10 * ub + g11 * vb);
+      };
+      const double gxx = quad(xp, xq, ux, vx, xp, xq, ux, vx);
+      const double gyy = quad(yp, yq, uy, vy, yp, yq, uy, vy);
+      const double gxy = quad(xp, xq, ux, vx, yp, yq, uy, vy);
+      double c, sn, rot;
+      plane_rot(gxx, gyy, gxy, tol2, c, sn, rot);
+      csn[2 * j] = c;
+      csn[2 * j + 1] = sn;
+      mo = fmax(mo, rot);
     }
     __syncthreads();
     double* tmp = cur;
@@ -519,7 +556,7 @@ jacobi_gram_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows, in
       }
     }
   }
-  if (tid < W && mo > 0.0) atomic_max_pos(info, mo);
+  if ((tid < W || tid >= NTH - W) && mo > 0.0) atomic_max_pos(info, mo);
   if (g_qr_dbg != nullptr && tid == 0 && blockIdx.x == 0) {
     tstamp[5] = clock64();
     for (int i = 0; i < 6; ++i) g_qr_dbg[2048 + i] = tstamp[i];
@@ -1086,8 +1123,8 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
     cudaFuncSetAttribute(jacobi_gram_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   }
   const int GW = gram_w;
-  const size_t need_gram = ((size_t)2 * GW * gld + 3 * 2 * GW * GLD + 2 * GW) * sizeof(double) +
-                           (size_t)(2 * GW - 1) * GW * sizeof(unsigned short);
+  const size_t need_gram = ((size_t)2 * GW * gld + 3 * 2 * GW * GLD + 4 * GW) * sizeof(double) +
+                           (size_t)(2 * GW - 1) * GW * sizeof(unsigned short) + (size_t)(2 * GW - 1) * 2 * GW + 16;
   const bool gram = use_gram && need_gram <= 220 * 1024 && ns > GW && gld <= 512 && (rows % 2 == 0) && (ns % 2 == 0);
   const int bw = gram ? GW : (Wd ? Wd : JW);
   const int nblk = (ns + bw - 1) / bw;
