@@ -146,6 +146,14 @@ int tnml_bond_update(tnml_handle h, int b, int ha, const tnml_bond_params* p,
  * outputs P (either may be NULL), from the last quadcost. */
 int tnml_predict(tnml_handle h, int32_t* labels_out, double* P_out /*[NT][10]*/);
 
+/* fullTest (util.h:123-200, driven by fulltest.cc:7-99): classify every image currently held
+ * by the handle with the MPS currently held (tnml_set_site): per image the full contraction
+ * toverlap(psi,img,cent) (util.h:19-40) and argmax_l |W_l| (util.h:160-169).  Implemented as
+ * right-environment build + one forward pass at bond 1, i.e. the same kernels as quadcost.
+ * pred_out (may be NULL) receives the predicted label of every image of this shard;
+ * *ncorrect the number of correct ones (all-reduced over ranks). */
+int tnml_fulltest(tnml_handle h, int32_t* pred_out, int64_t* ncorrect);
+
 /* Read an environment slot back (testing / checkpointing):
  * thin -> [NT][m], fat -> [NT][NL][m]. */
 int tnml_get_env(tnml_handle h, int slot, int* m, int* is_fat, double* data, size_t capacity_elems);

@@ -184,6 +184,16 @@ def toverlap(W, feat_n: np.ndarray, jc: int):
     return np.einsum("a,abl,b->l", l, Mc, r)
 
 
+def full_test(W, feat: np.ndarray, labels: np.ndarray):
+    """util.h:123-200 fullTest: per image W_l = toverlap(psi,img,cent), prediction
+    argmax_l |W_l| (first strict maximum).  Returns (ncorrect, predictions, outputs)."""
+    N = len(W) - 1
+    jc = [j for j in range(1, N + 1) if W[j].ndim == 4][0]
+    P = np.stack([toverlap(W, feat[n], jc) for n in range(feat.shape[0])])
+    pred = argmax_first(np.abs(P))
+    return int(np.sum(pred == np.asarray(labels))), pred, P
+
+
 # --------------------------------------------------------------------------
 # TrainStates (fixedL.cc:64-274), structured form
 # --------------------------------------------------------------------------

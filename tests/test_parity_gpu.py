@@ -264,6 +264,15 @@ def test_fixedL_binary_matches_capi(capi, tmp_path):
         assert res.newm == ms[k]
         assert abs(res.cost / 200 - costs[k]) < 2e-10 + 1e-9 * costs[k], k    # printed with 10 decimals
     assert "Before starting DMRG Cost" in r.stdout and "Writing W to disk" in r.stdout
+    # the trained W written by fixedL is then evaluated by the drop-in `fulltest` program
+    D.write_idx_files(str(tmp_path / "d"), u8, labels, side, kind="t10k")
+    ft = os.path.join(root, "tnml_b200", "host", "fulltest")
+    (tmp_path / "in_test").write_text(f"input\n{{\ndatadir = {tmp_path}/d\nimglen = {side}\n}}\n")
+    r2 = subprocess.run([ft, "in_test"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r2.returncode == 0, r2.stderr[-2000:]
+    mt = re.search(r"(\d+)/200 correct", r2.stdout)
+    assert mt and abs(int(mt.group(1)) - int(res.ncorrect)) <= 2     # same images, same final W
+    assert "Total # test images = 200" in r2.stdout
     h.close()
 
 
@@ -327,3 +336,23 @@ def test_cg_reuse_forward_option(capi, b):
     with pytest.raises(capi.TnmlError):
         h.set_option("no_such_option", 1)
     h.close()
+
+
+def test_fulltest_matches_oracle(capi):
+    """inference (fulltest.cc / util.h fullTest) on a held-out set after a sweep."""
+    feat, labels, W = make_problem(N=10, NT=900, m0=3)
+    tr, te = slice(0, 600), slice(600, 900)
+    h = _gpu_state(capi, feat[tr], labels[tr], W)
+    p = capi.BondParams(3, 0.0, 1e-10, 1e-10, 8, 4, 0)
+    for b, ha in O.sweep_schedule(10):
+        h.bond_update(b, ha, p)
+    Wt = h.get_mps()
+    h.close()
+    ncor_o, pred_o, P_o = O.full_test(Wt, feat[te], labels[te])
+    from tnml_b200 import fixedl
+    lines = []
+    ncor, pred = fixedl.fullTest(Wt, feat[te], labels[te].astype(np.int32), log=lines.append)
+    # near-ties of |P_l| may flip between the two summation orders
+    assert abs(ncor - ncor_o) <= 2 and np.sum(pred != pred_o) <= 3
+    assert lines[0].startswith(f"{ncor}/300 correct") and lines[-1] == "Total # test images = 300"
+    assert ncor > 60     # learned something (chance = 30)

@@ -53,7 +53,7 @@ SYMBOLS = [
     "tnml_version", "tnml_last_error", "tnml_create", "tnml_destroy", "tnml_set_images",
     "tnml_set_site", "tnml_get_site_dims", "tnml_get_site", "tnml_init_envs", "tnml_set_bond",
     "tnml_bond_form", "tnml_bond_dims", "tnml_bond_load", "tnml_bond_store", "tnml_cgrad",
-    "tnml_svd_split", "tnml_quadcost", "tnml_shift_env", "tnml_bond_update", "tnml_predict",
+    "tnml_svd_split", "tnml_quadcost", "tnml_shift_env", "tnml_bond_update", "tnml_predict", "tnml_fulltest",
     "tnml_get_env", "tnml_comm_get_unique_id", "tnml_comm_init_rank", "tnml_set_option", "tnml_get_stats",
     "tnml_set_timing", "tnml_synchronize", "tnml_stream",
 ]
@@ -93,6 +93,7 @@ def load_library():
     lib.tnml_shift_env.argtypes = [vp, i, i]
     lib.tnml_bond_update.argtypes = [vp, i, i, C.POINTER(BondParams), C.POINTER(BondResult)]
     lib.tnml_predict.argtypes = [vp, vp, vp]
+    lib.tnml_fulltest.argtypes = [vp, vp, C.POINTER(i64)]
     lib.tnml_get_env.argtypes = [vp, i, ip, ip, vp, C.c_size_t]
     lib.tnml_comm_get_unique_id.argtypes = [vp]
     lib.tnml_comm_init_rank.argtypes = [vp, i, i, vp]
@@ -226,6 +227,13 @@ class Handle:
         P = np.empty((self.NT, NL), np.float64) if want_P else None
         self._ck(self.lib.tnml_predict(self._h, _ptr(lab), _ptr(P) if want_P else None))
         return (lab, P) if want_P else lab
+
+    def fulltest(self):
+        """fullTest (util.h:123-200): returns (predicted labels, ncorrect)."""
+        pred = np.empty(self.NT, np.int32)
+        nc = C.c_int64()
+        self._ck(self.lib.tnml_fulltest(self._h, _ptr(pred), C.byref(nc)))
+        return pred, nc.value
 
     def get_env(self, slot):
         m, fat = C.c_int(), C.c_int()

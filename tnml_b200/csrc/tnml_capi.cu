@@ -945,6 +945,17 @@ int tnml_predict(tnml_handle h, int32_t* labels_out, double* P_out) {
   return TNML_OK;
 }
 
+int tnml_fulltest(tnml_handle h, int32_t* pred_out, int64_t* ncorrect) {
+  if (!h || h->N == 0) return h ? fail(h, TNML_ERR_INVALID, "no images") : TNML_ERR_INVALID;
+  TRY(tnml_init_envs(h));           // right environments of every image, then setBond(1)
+  double C = 0.0;
+  int64_t nc = 0;
+  TRY(tnml_quadcost(h, 1, 0.0, &C, nullptr, &nc));   // P = full contraction, argmax |P_l|
+  if (ncorrect) *ncorrect = nc;
+  if (pred_out) TRY(tnml_predict(h, pred_out, nullptr));
+  return TNML_OK;
+}
+
 int tnml_get_env(tnml_handle h, int slot, int* m, int* is_fat, double* data, size_t capacity_elems) {
   if (!h || slot < 1 || slot > h->N) return h ? fail(h, TNML_ERR_INVALID, "bad slot %d", slot) : TNML_ERR_INVALID;
   Slot& s = h->slot[slot];

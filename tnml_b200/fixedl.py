@@ -97,3 +97,26 @@ def mldmrg(ts: TrainStates, Nsweep, maxm, minm, cutoff, Npass=4, lam=0.0, cconv=
             if max_bonds is not None and len(out) >= max_bonds:
                 return out
     return out
+
+
+def fullTest(W, feat, labels, device=0, log=print):
+    """util.h:123-200 `fullTest` / fulltest.cc: classify a test set with the MPS W and print the
+    reference's report lines.  Returns (ncorrect, predictions)."""
+    h = capi.Handle(device)
+    h.set_images(feat, labels)
+    h.set_mps(W)
+    pred, ncor = h.fulltest()
+    h.close()
+    labels = np.asarray(labels)
+    nte = len(labels)
+    ninc = nte - ncor
+    if log:
+        log(f"{ncor}/{nte} correct ({ncor * 100.0 / nte:.2f}%), {ninc}/{nte} incorrect ({ninc * 100.0 / nte:.2f}%)")
+        for l in range(10):
+            nt = int(np.sum(labels == l))
+            if nt == 0:
+                continue
+            ni = int(np.sum((labels == l) & (pred != l)))
+            log(f"  Digit {l} {nt - ni}/{nt} correct ({(nt - ni) * 100.0 / nt:.2f}%), {ni}/{nt} incorrect ({ni * 100.0 / nt:.2f}%)")
+        log(f"Total # test images = {nte}")
+    return ncor, pred
