@@ -170,7 +170,9 @@ int tnml_comm_init_rank(tnml_handle h, int nranks, int rank, const uint8_t* id);
 /* Options (name, value).  "cg_reuse_forward" (default 0): 0 = every CG pass recomputes the
  * residual from scratch exactly like fixedL.cc:412-421; 1 = the forward outputs are updated
  * linearly, P(B + a p) = P(B) + a P(p) with P(p) taken from the pAp pass (fixedL.cc:393-402), and
- * only the backward half is re-evaluated -- same mathematics, 3 of 13 projection passes fewer. */
+ * only the backward half is re-evaluated -- same mathematics, 3 of 13 projection passes fewer.
+ * "reserve_m": environment slots are allocated for this link dimension so that they never have to
+ * grow during the sweeps (tnml_bond_update raises it to maxm by itself). */
 int tnml_set_option(tnml_handle h, const char* name, double value);
 
 /* Counters for the roofline report: kernel launches issued by this library,

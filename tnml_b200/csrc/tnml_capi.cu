@@ -111,6 +111,7 @@ struct tnml_handle_s {
   double* P = nullptr;  // [NT][NL]
   double* PV = nullptr; // [NT][NL]  p*v_n of the current CG pass (cg_reuse_forward)
   int cg_reuse_forward = 0;
+  int reserve_m = 0;       // env slots are sized for this link dim (set from maxm by tnml_bond_update)
   int32_t* pred = nullptr;
   double* stats_partial = nullptr;
   int nfat_blocks = 0;
@@ -451,11 +452,25 @@ int ddot(tnml_handle h, long n, const double* x, const double* y, double* out) {
   return fetch(h, h->dscal + 16, 1, out);
 }
 
-int alloc_slot(tnml_handle h, Slot& s, size_t bytes) {
+// `reserve` >= bytes: size to allocate when the slot has to grow.  During sweeps the link dims
+// grow towards maxm; growing a slot means a fresh cudaMallocAsync of up to 0.6 GB (measured:
+// 20 ms stalls on ~1 bond in 10 during the first sweeps), so slots are sized for maxm at once
+// while that fits comfortably in HBM.
+int alloc_slot(tnml_handle h, Slot& s, size_t bytes, size_t reserve) {
   if (s.p && s.bytes >= bytes) return 0;
   if (s.p) CK(cudaFreeAsync(s.p, h->st));
   s.p = nullptr;
   s.bytes = 0;
+  if (reserve > bytes) {
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && fr > reserve + (tot >> 3) &&
+        cudaMallocAsync(&s.p, reserve, h->st) == cudaSuccess) {
+      s.bytes = reserve;
+      return 0;
+    }
+    cudaGetLastError();
+    s.p = nullptr;
+  }
   CK(cudaMallocAsync(&s.p, bytes, h->st));
   s.bytes = bytes;
   return 0;
@@ -484,7 +499,8 @@ int advance_env(tnml_handle h, int c, int right) {
   const int outfat = (pe.fat || w.lab) ? 1 : 0;
   Slot& ns = h->slot[c];
   const size_t bytes = (size_t)NT * kout * (outfat ? NL : 1) * sizeof(double);
-  TRY(alloc_slot(h, ns, bytes));
+  const size_t reserve = (size_t)NT * std::max(kout, h->reserve_m) * (outfat ? NL : 1) * sizeof(double);
+  TRY(alloc_slot(h, ns, bytes, reserve));
   const double* Bm = w.d;
   PhaseTimer t(h, PH_SHIFT);
   if (right || w.lab) {
@@ -586,7 +602,7 @@ int tnml_destroy(tnml_handle h) {
     if (b->p) cudaFree(b->p);
   void* ptrs[] = {h->feat, h->labels, h->ones, h->P, h->PV, h->pred, h->stats_partial, h->dscal, h->dot_scratch,
                   h->svd.X, h->svd.J, h->svd.sig2, h->svd.perm, h->svd.info, h->svd.flags,
-                  h->svd.M, h->svd.tau, h->svd.ready, h->svd.Y};
+                  h->svd.M, h->svd.tau, h->svd.ready, h->svd.Y, h->svd.M2, h->svd.tau2, h->svd.Y2, h->svd.perm0};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->svd.gexec) cudaGraphExecDestroy(h->svd.gexec);
@@ -912,6 +928,7 @@ int tnml_bond_update(tnml_handle h, int b, int ha, const tnml_bond_params* p, tn
   if (ha != 1 && ha != 2) return fail(h, TNML_ERR_INVALID, "ha must be 1 or 2");
   tnml_bond_result res;
   memset(&res, 0, sizeof(res));
+  if (p->maxm > h->reserve_m) h->reserve_m = p->maxm;
   TRY(tnml_set_bond(h, b));                                            // 488
   TRY(tnml_bond_form(h));                                              // 493-498
   res.origm = h->W[b].mr;
@@ -1003,6 +1020,10 @@ int tnml_set_option(tnml_handle h, const char* name, double value) {
   if (!h || !name) return TNML_ERR_INVALID;
   if (strcmp(name, "cg_reuse_forward") == 0) {
     h->cg_reuse_forward = (value != 0.0);
+    return TNML_OK;
+  }
+  if (strcmp(name, "reserve_m") == 0) {
+    h->reserve_m = (int)value;
     return TNML_OK;
   }
   return fail(h, TNML_ERR_INVALID, "unknown option %s", name);

@@ -85,7 +85,13 @@ struct SvdWork {
   int* ready = nullptr;    // [ns] dataflow flags
   double* Y = nullptr;     // [kept][nb] big-side unit vectors
   long capM = 0, capY = 0;
-  int use_qr = -1;         // -1 auto, 0 never, 1 always (TNML_SVD_QR)
+  // second QR (R1^T = Q2 R2, Jacobi on R2^T) + column sort
+  double* M2 = nullptr;    // [ns][ns] R2^T, then its rotated columns
+  double* tau2 = nullptr;  // [ns]
+  double* Y2 = nullptr;    // [kept][ns] small-side unit vectors (before the column permutation)
+  int* perm0 = nullptr;    // [ns] columns of X sorted by decreasing norm
+  long capM2 = 0;
+  int use_qr = -1;         // -1 auto, 0 never, 1 one QR, 3 sort + two QRs (TNML_SVD_QR)
   cudaGraphExec_t gexec = nullptr;   // one Jacobi sweep, captured for the current (buffers, dims)
   long gkey[6] = {0, 0, 0, 0, 0, 0};
 };

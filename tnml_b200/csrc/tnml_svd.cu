@@ -338,8 +338,9 @@ __device__ __forceinline__ void dmma884s(double& d0, double& d1, double a, doubl
                : "d"(a), "d"(b));
 }
 
-// Branch-free (two of them are evaluated per thread and must interleave).  rot = 1 when a
-// rotation is applied, 0 when the pair is already orthogonal to tolerance.
+// Branch-free (two of them are evaluated per thread and must interleave).  rot = cos^2 of the
+// angle between the two columns when a rotation is applied, 0 when the pair is already
+// orthogonal to tolerance.
 __device__ __forceinline__ void plane_rot(double a, double b, double g, double tol2, double& c, double& s,
                                           double& rot) {
   const double ab = a * b, gg = g * g;
@@ -353,7 +354,7 @@ __device__ __forceinline__ void plane_rot(double a, double b, double g, double t
   const double ss = copysign(0.5, d) * h * rinv * rc;
   c = doit ? cc : 1.0;
   s = doit ? ss : 0.0;
-  rot = doit ? 1.0 : 0.0;
+  rot = doit ? gg / ab : 0.0;   // cos^2 of the angle that was rotated away (0: no rotation)
 }
 
 constexpr int GLD = 36;   // leading dimension of the 32 x 32 Gram / rotation matrices in smem
@@ -966,19 +967,27 @@ __global__ void rt_form_kernel(const double* __restrict__ X, int nb, int ns, dou
 }
 
 // big-side unit vectors: Y[i] = Q * [J'[:, perm[i]]; 0].  One warp per kept vector.
+// scale_sig2 != nullptr: the source column is sigma * unit vector, normalise it (zero if sigma = 0);
+// rowperm != nullptr: out[rowperm[r]] = y[r] (undo the column sort of the first QR).
 template <int RPL>
 __global__ void __launch_bounds__(256)
 apply_q_kernel(const double* __restrict__ X, const double* __restrict__ tau, const double* __restrict__ Jm,
-               const int* __restrict__ perm, int nb, int ns, int m, double* __restrict__ Y) {
+               const int* __restrict__ perm, int nb, int ns, int m, double* __restrict__ Y,
+               const double* __restrict__ scale_sig2, const int* __restrict__ rowperm) {
   const int lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (i0 >= m) return;
   const double* jc = Jm + (long)perm[i0] * ns;
+  double sc = 1.0;
+  if (scale_sig2 != nullptr) {
+    const double sg = sqrt(scale_sig2[perm[i0]]);
+    sc = (sg > 0.0) ? 1.0 / sg : 0.0;
+  }
   double y[RPL];
 #pragma unroll
   for (int i = 0; i < RPL; ++i) {
     int r = lane + 32 * i;
-    y[i] = (r < ns) ? jc[r] : 0.0;
+    y[i] = (r < ns) ? jc[r] * sc : 0.0;
   }
   double vn[RPL];
   double tn = 0.0;
@@ -1010,8 +1019,70 @@ apply_q_kernel(const double* __restrict__ X, const double* __restrict__ tau, con
 #pragma unroll
   for (int i = 0; i < RPL; ++i) {
     int r = lane + 32 * i;
-    if (r < nb) out[r] = y[i];
+    if (r < nb) out[rowperm ? rowperm[r] : r] = y[i];
   }
+}
+
+// ---- column sort (cheap substitute for pivoting) + second QR --------------------------------
+// perm0[rank] = column with the rank-th largest norm (stable).  One CTA.
+__global__ void __launch_bounds__(1024)
+svd_colsort_kernel(const double* __restrict__ X, int nb, int ns, double* __restrict__ nrm2, int* __restrict__ perm0) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = warp; c < ns; c += 32) {
+    const double* x = X + (long)c * nb;
+    double a = 0.0;
+    for (int r = lane; r < nb; r += 32) a = fma(x[r], x[r], a);
+    a = wsum(a);
+    if (lane == 0) nrm2[c] = a;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < ns; c += blockDim.x) {
+    const double v = nrm2[c];
+    int rank = 0;
+    for (int k = 0; k < ns; ++k) {
+      const double u = nrm2[k];
+      rank += (u > v || (u == v && k < c)) ? 1 : 0;
+    }
+    perm0[rank] = c;
+  }
+}
+
+__global__ void svd_permute_cols_kernel(const double* __restrict__ src, int nb, int ns, const int* __restrict__ perm0,
+                                        double* __restrict__ dst) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)nb * ns) return;
+  const int r = (int)(idx % nb), c = (int)(idx / nb);
+  dst[idx] = src[(long)perm0[c] * nb + r];
+}
+
+// two-QR path scatter: both sides are unit vectors (Y: [k][nb] big side, Y2: [k][ns] small side)
+__global__ void svd_scatter_qr2_kernel(const double* __restrict__ Y, const double* __restrict__ Y2,
+                                       const double* __restrict__ sig2, const int* __restrict__ perm, SvdGeom sg,
+                                       int isoIsA, int m, double* __restrict__ Wb, double* __restrict__ Wb1) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long nAm = (long)sg.nA * m, nBm = (long)sg.nB * m;
+  if (idx >= nAm + nBm) return;
+  const bool sideA = idx < nAm;
+  long e = sideA ? idx : idx - nAm;
+  int k, i;
+  if (sideA) {
+    int l = (int)(e % sg.nlA);
+    long r = e / sg.nlA;
+    k = (int)(r % m);
+    int as = (int)(r / m);
+    i = as * sg.nlA + l;
+  } else {
+    k = (int)(e / sg.nB);
+    i = (int)(e % sg.nB);
+  }
+  const bool thisIsBig = (sideA == (sg.bigIsA != 0));
+  const bool thisIsIso = (sideA == (isoIsA != 0));
+  double v = thisIsBig ? Y[(long)k * sg.nb + i] : Y2[(long)k * sg.ns + i];
+  if (!thisIsIso) v *= sqrt(sig2[perm[k]]);
+  if (sideA)
+    Wb[e] = v;
+  else
+    Wb1[e] = v;
 }
 
 // QR path scatter: big side = unit vectors Y[k][nb]; small side = columns of M (sigma-scaled)
@@ -1084,6 +1155,17 @@ static int ensure(SvdWork& w, long nX, int ns) {
     if (cudaMalloc(&w.Y, nX * sizeof(double)) != cudaSuccess) return -1;
     w.capY = nX;
   }
+  if (nJ > w.capM2) {   // two-QR path
+    if (w.M2) cudaFree(w.M2);
+    if (w.tau2) cudaFree(w.tau2);
+    if (w.Y2) cudaFree(w.Y2);
+    if (w.perm0) cudaFree(w.perm0);
+    if (cudaMalloc(&w.M2, nJ * sizeof(double)) != cudaSuccess) return -1;
+    if (cudaMalloc(&w.tau2, ns * sizeof(double)) != cudaSuccess) return -1;
+    if (cudaMalloc(&w.Y2, nJ * sizeof(double)) != cudaSuccess) return -1;
+    if (cudaMalloc(&w.perm0, ns * sizeof(int)) != cudaSuccess) return -1;
+    w.capM2 = nJ;
+  }
   return 0;
 }
 
@@ -1129,7 +1211,16 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
   const int bw = gram ? GW : (Wd ? Wd : JW);
   const int nblk = (ns + bw - 1) / bw;
   const int nblk_e = (nblk % 2) ? nblk + 1 : nblk;
-  const double conv = gram ? 0.5 : (Wd ? tol2 : tol);   // gram: 'a rotation happened' flag; smem kernels: off^2
+  // gram: largest cos^2 rotated away during the sweep.  Cyclic Jacobi converges quadratically, so a
+  // sweep whose largest angle had |cos| <= 1e-8 leaves every pair orthogonal to ~1e-16: no extra
+  // "clean" sweep is needed to confirm (measured on bond matrices: ... 1e-5, 1e-10, 0).
+  // smem kernels: off^2.
+  static double gram_conv = -1.0;
+  if (gram_conv < 0.0) {
+    const char* e = getenv("TNML_SVD_STOP");
+    gram_conv = e ? atof(e) : 1e-16;
+  }
+  const double conv = gram ? gram_conv : (Wd ? tol2 : tol);
   const int max_sweeps = 60;
   int hflag = 0;
   for (int sw = 0; sw < max_sweeps && !hflag; ++sw) {
@@ -1174,7 +1265,7 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
         enqueue();
       }
       nl += nblk_e;
-      if (sw >= 6) {
+      if (sw >= 3) {
         if (cudaMemcpyAsync(&hflag, w.flags, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
         if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
       }
@@ -1212,10 +1303,10 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
 }
 
 template <int RPL>
-static void launch_qr(cudaStream_t st, SvdWork& w, int nb, int ns) {
-  qr_dataflow_kernel<RPL><<<(ns + 7) / 8, 256, 0, st>>>(w.X, nb, ns, w.tau, w.ready);
+static void launch_qr(cudaStream_t st, SvdWork& w, double* Xq, double* tau, int nb, int ns) {
+  qr_dataflow_kernel<RPL><<<(ns + 7) / 8, 256, 0, st>>>(Xq, nb, ns, tau, w.ready);
 }
-static void launch_qr_block8(cudaStream_t st, SvdWork& w, int nb, int ns) {
+static void launch_qr_block8(cudaStream_t st, SvdWork& w, double* Xq, double* tau, int nb, int ns) {
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(qr_block_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
@@ -1231,7 +1322,7 @@ static void launch_qr_block8(cudaStream_t st, SvdWork& w, int nb, int ns) {
       cudaMemcpyToSymbol(g_qr_dbg, &dbg, sizeof(dbg));
     }
   }
-  qr_block_kernel<8><<<(ns + 31) / 32, 1024, sh, st>>>(w.X, nb, ns, w.tau, w.ready);
+  qr_block_kernel<8><<<(ns + 31) / 32, 1024, sh, st>>>(Xq, nb, ns, tau, w.ready);
   if (dbg_on) {
     cudaStreamSynchronize(st);
     std::vector<long long> hd(ns * 4);
@@ -1260,8 +1351,25 @@ static void launch_qr_block8(cudaStream_t st, SvdWork& w, int nb, int ns) {
   }
 }
 template <int RPL>
-static void launch_apply_q(cudaStream_t st, SvdWork& w, int nb, int ns, int m) {
-  apply_q_kernel<RPL><<<(m + 7) / 8, 256, 0, st>>>(w.X, w.tau, w.J, w.perm, nb, ns, m, w.Y);
+static void launch_apply_q(cudaStream_t st, const double* Xq, const double* tau, const double* src, const int* perm,
+                           int nb, int ns, int m, double* Yout, const double* scale_sig2, const int* rowperm) {
+  apply_q_kernel<RPL><<<(m + 7) / 8, 256, 0, st>>>(Xq, tau, src, perm, nb, ns, m, Yout, scale_sig2, rowperm);
+}
+// Householder QR of the column-major nb x ns matrix Xq in place (reflectors below the diagonal)
+static int run_qr(cudaStream_t st, SvdWork& w, double* Xq, double* tau, int nb, int ns) {
+  if (cudaMemsetAsync(w.ready, 0, ns * sizeof(int), st) != cudaSuccess) return -2;
+  if (nb <= 32 * 8) launch_qr_block8(st, w, Xq, tau, nb, ns);
+  else if (nb <= 32 * 20) launch_qr<20>(st, w, Xq, tau, nb, ns);
+  else if (nb <= 32 * 40) launch_qr<40>(st, w, Xq, tau, nb, ns);
+  else launch_qr<96>(st, w, Xq, tau, nb, ns);
+  return 0;
+}
+static void run_apply_q(cudaStream_t st, const double* Xq, const double* tau, const double* src, const int* perm,
+                        int nb, int ns, int m, double* Yout, const double* scale_sig2, const int* rowperm) {
+  if (nb <= 32 * 8) launch_apply_q<8>(st, Xq, tau, src, perm, nb, ns, m, Yout, scale_sig2, rowperm);
+  else if (nb <= 32 * 20) launch_apply_q<20>(st, Xq, tau, src, perm, nb, ns, m, Yout, scale_sig2, rowperm);
+  else if (nb <= 32 * 40) launch_apply_q<40>(st, Xq, tau, src, perm, nb, ns, m, Yout, scale_sig2, rowperm);
+  else launch_apply_q<96>(st, Xq, tau, src, perm, nb, ns, m, Yout, scale_sig2, rowperm);
 }
 
 int svd_split(cudaStream_t st, SvdWork& w, const double* Bc, BondGeom g, int dir, double cutoff, int maxm,
@@ -1281,32 +1389,44 @@ int svd_split(cudaStream_t st, SvdWork& w, const double* Bc, BondGeom g, int dir
   long nl = 0;
   if (w.use_qr < 0) {
     const char* e = getenv("TNML_SVD_QR");
-    w.use_qr = e ? atoi(e) : 2;   // 2 = auto
+    w.use_qr = e ? atoi(e) : 2;   // 2 = auto (sort + two QRs from 32 columns on)
   }
   // QR preconditioning pays off from a few dozen columns on; it needs one resident warp per
   // column and the column in registers (nb <= 32*96)
-  const bool qr = (w.use_qr == 1 || (w.use_qr == 2 && ns >= 32)) && nb <= 32 * 96 && ns <= 8 * 140;
+  const bool qr = (w.use_qr == 1 || w.use_qr == 3 || (w.use_qr == 2 && ns >= 32)) && nb <= 32 * 96 && ns <= 8 * 140;
 
   long nJ = (long)ns * ns;
   long ninit = nJ > 8 ? nJ : 8;
-  svd_init_kernel<<<(unsigned)((ninit + 255) / 256), 256, 0, st>>>(w.J, ns, w.info, w.flags);
   long nX = (long)nb * ns;
-  svd_gather_kernel<<<(unsigned)((nX + 255) / 256), 256, 0, st>>>(Bc, sg, w.X);
-  nl += 2;
-
+  // 3 = column sort + two QRs (X P0 = Q1 R1, R1^T = Q2 R2, Jacobi on R2^T): about half the Jacobi
+  // sweeps of the one-QR path on freshly optimised bond matrices (tools/jacobi_precond_study.py)
+  const bool qr2 = qr && (w.use_qr == 2 || w.use_qr == 3);
+  svd_init_kernel<<<(unsigned)((ninit + 255) / 256), 256, 0, st>>>(w.J, ns, w.info, w.flags);
+  nl += 1;
   int rc;
-  if (qr) {
-    if (cudaMemsetAsync(w.ready, 0, ns * sizeof(int), st) != cudaSuccess) return -2;
-    if (nb <= 32 * 8) launch_qr_block8(st, w, nb, ns);
-    else if (nb <= 32 * 20) launch_qr<20>(st, w, nb, ns);
-    else if (nb <= 32 * 40) launch_qr<40>(st, w, nb, ns);
-    else launch_qr<96>(st, w, nb, ns);
+  if (qr2) {
+    svd_gather_kernel<<<(unsigned)((nX + 255) / 256), 256, 0, st>>>(Bc, sg, w.Y);
+    svd_colsort_kernel<<<1, 1024, 0, st>>>(w.Y, nb, ns, w.sig2, w.perm0);
+    svd_permute_cols_kernel<<<(unsigned)((nX + 255) / 256), 256, 0, st>>>(w.Y, nb, ns, w.perm0, w.X);
+    if (run_qr(st, w, w.X, w.tau, nb, ns) != 0) return -2;
     rt_form_kernel<<<(unsigned)((nJ + 255) / 256), 256, 0, st>>>(w.X, nb, ns, w.M);
-    nl += 3;
+    if (run_qr(st, w, w.M, w.tau2, ns, ns) != 0) return -2;
+    rt_form_kernel<<<(unsigned)((nJ + 255) / 256), 256, 0, st>>>(w.M, ns, ns, w.M2);
+    nl += 9;
+    rc = jacobi_iterate(st, w, w.M2, w.J, ns, ns, nl);
+    if (rc == -2) return rc;
+    svd_finalize_kernel<<<1, 1024, 0, st>>>(w.M2, ns, ns, w.sig2, w.perm, cutoff, maxm, minm, do_rel_cutoff, w.info);
+  } else if (qr) {
+    svd_gather_kernel<<<(unsigned)((nX + 255) / 256), 256, 0, st>>>(Bc, sg, w.X);
+    if (run_qr(st, w, w.X, w.tau, nb, ns) != 0) return -2;
+    rt_form_kernel<<<(unsigned)((nJ + 255) / 256), 256, 0, st>>>(w.X, nb, ns, w.M);
+    nl += 4;
     rc = jacobi_iterate(st, w, w.M, w.J, ns, ns, nl);
     if (rc == -2) return rc;
     svd_finalize_kernel<<<1, 1024, 0, st>>>(w.M, ns, ns, w.sig2, w.perm, cutoff, maxm, minm, do_rel_cutoff, w.info);
   } else {
+    svd_gather_kernel<<<(unsigned)((nX + 255) / 256), 256, 0, st>>>(Bc, sg, w.X);
+    nl += 1;
     rc = jacobi_iterate(st, w, w.X, w.J, nb, ns, nl);
     if (rc == -2) return rc;
     svd_finalize_kernel<<<1, 1024, 0, st>>>(w.X, nb, ns, w.sig2, w.perm, cutoff, maxm, minm, do_rel_cutoff, w.info);
@@ -1321,11 +1441,16 @@ int svd_split(cudaStream_t st, SvdWork& w, const double* Bc, BondGeom g, int dir
   *sweeps = (int)hinfo[3];
   const int isoIsA = (dir == 1) ? 1 : 0;
   long nout = (long)(sg.nA + sg.nB) * m;
-  if (qr) {
-    if (nb <= 32 * 8) launch_apply_q<8>(st, w, nb, ns, m);
-    else if (nb <= 32 * 20) launch_apply_q<20>(st, w, nb, ns, m);
-    else if (nb <= 32 * 40) launch_apply_q<40>(st, w, nb, ns, m);
-    else launch_apply_q<96>(st, w, nb, ns, m);
+  if (qr2) {
+    // X P0 = Q1 W Sigma (Q2 J)^T with W Sigma = the rotated columns of R2^T:
+    // big side = Q1 [W; 0], small side = P0 (Q2 J)
+    run_apply_q(st, w.X, w.tau, w.M2, w.perm, nb, ns, m, w.Y, w.sig2, nullptr);
+    run_apply_q(st, w.M, w.tau2, w.J, w.perm, ns, ns, m, w.Y2, nullptr, w.perm0);
+    svd_scatter_qr2_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(w.Y, w.Y2, w.sig2, w.perm, sg, isoIsA, m,
+                                                                        Wb_out, Wb1_out);
+    nl += 3;
+  } else if (qr) {
+    run_apply_q(st, w.X, w.tau, w.J, w.perm, nb, ns, m, w.Y, nullptr, nullptr);
     svd_scatter_qr_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(w.Y, w.M, w.sig2, w.perm, sg, isoIsA, m,
                                                                        Wb_out, Wb1_out);
     nl += 2;

@@ -42,9 +42,12 @@ class TrainStates:
     def size(self):
         return self.NT
 
-    def init(self, W):
-        """fixedL.cc:122-157."""
+    def init(self, W, reserve_m=0):
+        """fixedL.cc:122-157.  reserve_m (normally maxm): size the environment slots for that link
+        dimension at once so they never have to grow during the sweeps."""
         self.h.set_mps(W)
+        if reserve_m:
+            self.h.set_option("reserve_m", reserve_m)
         self.h.init_envs()
 
     def setBond(self, b):

@@ -135,6 +135,8 @@ class TrainStates {
     W.setA(j, ITensor(is, std::move(d)));
   }
 
+  // size the environment slots for link dimension m so that they never grow during the sweeps
+  void reserve(int m) { TN(tnml_set_option(h_, "reserve_m", (double)m)); }
   void init(MPS const& W) {  // fixedL.cc:122-157
     for (int j = 1; j <= N; ++j) upload(W, j);
     TN(tnml_init_envs(h_));
@@ -494,6 +496,7 @@ int main(int argc, const char* argv[]) {
 
     // Project training states (product states) into environment of W MPS
     printf("Projecting training states...");
+    ts.reserve(maxm);
     ts.init(W);
     println("done");
 

@@ -76,7 +76,7 @@ def sweeps(NT, maxm, nsweep, tag):
     feat = data.phi(pix)
     W = data.random_mps(196, 2, 10, seed=3)
     ts = fixedl.TrainStates(feat, labels)
-    ts.init(W)
+    ts.init(W, reserve_m=maxm)
     say(f"== {tag}: synthetic 14x14, NT={NT}, maxm={maxm} minm={max(10, maxm // 2)}, Npass=4, start m=10")
     p = capi.BondParams(4, 0.0, 1e-10, 1e-10, maxm, max(10, maxm // 2), 0)
     for sw in range(1, nsweep + 1):
