@@ -16,7 +16,7 @@ $(LIB): $(CSRC) $(wildcard tnml_b200/csrc/*.cuh) include/tnml_b200.h
 host: $(HOSTBIN) tnml_b200/host/fulltest
 tnml_b200/host/fulltest: tnml_b200/host/fulltest.cc tnml_b200/host/itensor_lite.h tnml_b200/host/mnist.h include/tnml_b200.h $(LIB)
 	$(CXX) -O2 -std=c++17 -Wall -o $@ tnml_b200/host/fulltest.cc -Ltnml_b200 -ltnml_b200 -Wl,-rpath,'$$ORIGIN/..' -pthread
-$(HOSTBIN): tnml_b200/host/fixedL.cc tnml_b200/host/itensor_lite.h tnml_b200/host/mnist.h include/tnml_b200.h $(LIB)
+$(HOSTBIN): tnml_b200/host/fixedL.cc tnml_b200/host/initial_w.h tnml_b200/host/itensor_lite.h tnml_b200/host/mnist.h include/tnml_b200.h $(LIB)
 	$(CXX) -O2 -std=c++17 -Wall -o $@ tnml_b200/host/fixedL.cc -Ltnml_b200 -ltnml_b200 -Wl,-rpath,'$$ORIGIN/..' -pthread
 
 # CPU restatement used as checker / baseline only (never by the product)

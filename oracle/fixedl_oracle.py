@@ -550,3 +550,89 @@ def synthetic_pixels(NT: int, npix: int, seed: int = 20260925, first: int = 0):
     pix = np.where(u < 0.81, 0, 1 + np.floor(v * 255)).astype(np.uint8)
     labels = (np.arange(first, first + NT) % NL).astype(np.int64)
     return pix, labels
+
+
+# --------------------------------------------------------------------------
+# initial W (fixedL.cc:682-728, util.h:76-121) -- checker for
+# tnml_b200/host/initial_w.h.  ITensor's sum(vector<MPS>,args) ASSUMED as in
+# pairwise direct sums, each followed by orthogonalize(args)
+# (left half sweep without truncation, right half sweep truncating with the
+# SVD rule of truncate_spectrum).  Raw MPS = list (1-indexed) of [ml, p, mr].
+# --------------------------------------------------------------------------
+def mps_product_state(feat_n: np.ndarray):
+    """util.h:76-102 makeMPS: feat_n [N, d] -> bond-dimension-1 MPS."""
+    return [None] + [feat_n[j].reshape(1, -1, 1).copy() for j in range(feat_n.shape[0])]
+
+
+def mps_direct_sum(A, B):
+    N = len(A) - 1
+    C = [None]
+    for j in range(1, N + 1):
+        x, y = A[j], B[j]
+        ml = 1 if j == 1 else x.shape[0] + y.shape[0]
+        mr = 1 if j == N else x.shape[2] + y.shape[2]
+        z = np.zeros((ml, x.shape[1], mr))
+        lo = 0 if j == 1 else x.shape[0]
+        ro = 0 if j == N else x.shape[2]
+        z[:x.shape[0], :, :x.shape[2]] += x
+        z[lo:lo + y.shape[0], :, ro:ro + y.shape[2]] += y
+        C.append(z)
+    return C
+
+
+def mps_orthogonalize(W, cutoff, maxm, do_rel_cutoff=False):
+    N = len(W) - 1
+    for j in range(N, 1, -1):
+        ml, p, mr = W[j].shape
+        U, s, Vt = np.linalg.svd(W[j].reshape(ml, p * mr), full_matrices=False)
+        k = max(1, int(np.sum(s > 1e-14 * s[0])))
+        W[j] = Vt[:k].reshape(k, p, mr)
+        W[j - 1] = np.tensordot(W[j - 1], U[:, :k] * s[:k], axes=([2], [0]))
+    for j in range(1, N):
+        ml, p, mr = W[j].shape
+        U, s, Vt = np.linalg.svd(W[j].reshape(ml * p, mr), full_matrices=False)
+        m, _ = truncate_spectrum(s * s, maxm, 1, cutoff, do_rel_cutoff)
+        W[j] = U[:, :m].reshape(ml, p, m)
+        W[j + 1] = np.tensordot(s[:m, None] * Vt[:m], W[j + 1], axes=([1], [0]))
+    return W
+
+
+def mps_sum(terms, cutoff, maxm, do_rel_cutoff=False):
+    if len(terms) == 1:
+        return terms[0]
+    if len(terms) == 2:
+        return mps_orthogonalize(mps_direct_sum(terms[0], terms[1]), cutoff, maxm, do_rel_cutoff)
+    nt = [mps_orthogonalize(mps_direct_sum(terms[n], terms[n + 1]), cutoff, maxm, do_rel_cutoff)
+          for n in range(0, len(terms) - 1, 2)]
+    if len(terms) % 2 == 1:
+        nt.append(terms[-1])
+    return mps_sum(nt, cutoff, maxm, do_rel_cutoff)
+
+
+def mps_overlap(A, B):
+    E = np.ones((1, 1))
+    for j in range(1, len(A)):
+        E = np.einsum("ab,asc,bsd->cd", E, A[j], B[j])
+    return float(E[0, 0])
+
+
+def initial_w_sum(feat: np.ndarray, picks, jc: int, do_rel_cutoff=False):
+    """fixedL.cc:702-728 given the drawn image positions `picks[label] = [n, ...]`.
+    Returns W in the site-tensor layout of the rest of the oracle
+    ([ml,d,mr], label site [ml,d,mr,NL])."""
+    d = feat.shape[2]
+    ipsis = []
+    for lab in range(NL):
+        psis = [mps_product_state(feat[n]) for n in picks[lab]]
+        s = mps_sum(psis, 1e-10, 10, do_rel_cutoff)
+        A = s[jc]
+        T = np.zeros((A.shape[0], d, NL, A.shape[2]))
+        T[:, :, lab, :] = 0.1 * A                       # Aref(c) *= 0.1*setElt(L(1+label))
+        s[jc] = T.reshape(A.shape[0], d * NL, A.shape[2])
+        ipsis.append(s)
+    R = mps_sum(ipsis, 1e-8, 10, do_rel_cutoff)
+    R[jc] = R[jc] / np.linalg.norm(R[jc])                # W.Aref(c) /= norm(W.A(c))
+    W = [None] + [np.ascontiguousarray(R[j]) for j in range(1, len(R))]
+    A = R[jc]
+    W[jc] = np.ascontiguousarray(np.transpose(A.reshape(A.shape[0], d, NL, A.shape[2]), (0, 1, 3, 2)))
+    return W

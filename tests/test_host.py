@@ -98,6 +98,88 @@ def test_fixedL_fails_loudly_without_gpu(tmp_path):
     assert r.returncode != 0 and "not commensurate" in r.stderr
 
 
+def test_initial_w_sum_matches_oracle(tmp_path):
+    """the initial W (fixedL.cc:702-728: per label a compressed sum of `ninitial`
+    random product states, tagged 0.1*setElt(L), the ten summed, centre normalised) built by the
+    host program equals the oracle's restatement for the same drawn images, and equals the exact
+    (uncompressed) sum of product states up to the truncation error.  No GPU needed: `init_only`."""
+    from oracle import fixedl_oracle as O
+    from tnml_b200 import data
+    side, per, nini = 6, 12, 7
+    N = side * side
+    pix, labels = data.synthetic_digits(10 * per, side, seed=5)
+    u8 = (pix * 255).round().astype(np.uint8)
+    data.write_idx_files(str(tmp_path / "d"), u8, labels, side)
+    (tmp_path / "in").write_text(f"input\n{{\ndatadir = {tmp_path}/d\nNtrain = {per}\nimglen = {side}\nNbatch = 4\n"
+                                 f"ninitial = {nini}\nseed = 9\ninit_only = yes\n}}\n")
+    r = subprocess.run([_host_bin(), "in"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Summing %d random label 3 states" % nini in r.stdout and "Summing all 10 label states together" in r.stdout
+    picks = [[int(x) for x in re.search(r"label %d picks:([ 0-9]+)" % l, r.stdout).group(1).split()] for l in range(10)]
+    assert all(len(p) == nini for p in picks)
+    sel = np.array([labels[i] for i in range(len(labels))])
+    for l in range(10):
+        assert all(sel[i] == l for i in picks[l])             # randImg retries until the label matches
+    feat = data.phi(u8.astype(np.float64) / 255.0)            # same double /255 as the host (SURVEY F5)
+    jc = N // 2
+    Wh = data.read_mps_file(str(tmp_path / "W"))
+    Wo = O.initial_w_sum(feat, picks, jc)
+    assert Wh[jc].ndim == 4 and Wh[jc].shape[3] == 10 and abs(np.linalg.norm(Wh[jc]) - 1.0) < 1e-12
+
+    def raw(W):   # label site -> [ml, d*NL, mr] so that the overlap runs over the label index too
+        R = list(W)
+        A = W[jc]
+        R[jc] = np.transpose(A, (0, 1, 3, 2)).reshape(A.shape[0], -1, A.shape[2])
+        return R
+    hh, oo, ho = O.mps_overlap(raw(Wh), raw(Wh)), O.mps_overlap(raw(Wo), raw(Wo)), O.mps_overlap(raw(Wh), raw(Wo))
+    assert abs(ho / np.sqrt(hh * oo) - 1.0) < 1e-9            # same state (gauge free)
+    assert abs(hh / oo - 1.0) < 1e-9
+    assert max(w.shape[2] for w in Wh[1:]) <= 10              # Maxm = 10
+    # against the exact sum: W(x)_l  ~  0.1/norm * sum_{n in picks[l]} prod_j <phi(x_j)|phi(n_j)>
+    x = feat[:40]
+    Pw = np.array([O.toverlap(Wh, x[i], jc) for i in range(len(x))])
+    ex = np.stack([np.prod(np.einsum("ijs,njs->inj", x, feat[picks[l]]), axis=2).sum(1) for l in range(10)], axis=1)
+    scale = (Pw * ex).sum() / (ex * ex).sum()
+    assert np.abs(Pw - scale * ex).max() < 1e-3 * np.abs(Pw).max()
+
+
+def test_w0_to_w9_merge_matches_oracle(tmp_path):
+    """fixedL.cc:682-701: separate label MPS W0..W9 are tagged with setElt(L(label)) on site c and
+    summed with Cutoff 1E-10."""
+    from oracle import fixedl_oracle as O
+    from tnml_b200 import data
+    side = 4
+    N, jc = side * side, side * side // 2
+    pix, labels = data.synthetic_digits(40, side, seed=2)
+    data.write_idx_files(str(tmp_path / "d"), (pix * 255).round().astype(np.uint8), labels, side)
+    data.write_sites_file(str(tmp_path / "sites"), N)
+    rng = np.random.default_rng(0)
+    terms = []
+    for l in range(10):
+        dims = [1] + [min(3, 2 ** min(j, N - j)) for j in range(1, N)] + [1]
+        Wl = [None] + [rng.standard_normal((dims[j - 1], 2, dims[j])) / np.sqrt(dims[j - 1]) for j in range(1, N + 1)]
+        data.write_mps_file(str(tmp_path / f"W{l}"), Wl)
+        T = [None] + [w.copy() for w in Wl[1:]]
+        A = T[jc]
+        Z = np.zeros((A.shape[0], 2, 10, A.shape[2]))
+        Z[:, :, l, :] = A
+        T[jc] = Z.reshape(A.shape[0], 20, A.shape[2])
+        terms.append(T)
+    (tmp_path / "in").write_text(f"input\n{{\ndatadir = {tmp_path}/d\nNtrain = 4\nimglen = {side}\nNbatch = 4\n"
+                                 f"init_only = yes\n}}\n")
+    r = subprocess.run([_host_bin(), "in"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "Found separate W0,W1,...,W9 MPS: summing" in r.stdout, r.stderr[-2000:]
+    Wh = data.read_mps_file(str(tmp_path / "W"))
+    Ro = O.mps_sum(terms, 1e-10, 10 ** 6)
+    Rh = list(Wh)
+    A = Wh[jc]
+    Rh[jc] = np.transpose(A, (0, 1, 3, 2)).reshape(A.shape[0], -1, A.shape[2])
+    hh, oo, ho = O.mps_overlap(Rh, Rh), O.mps_overlap(Ro, Ro), O.mps_overlap(Rh, Ro)
+    assert abs(ho / np.sqrt(hh * oo) - 1.0) < 1e-10 and abs(hh / oo - 1.0) < 1e-10
+    exact = sum(O.mps_overlap(a, b) for a in terms for b in terms)      # |sum_l psi_l (x) e_l|^2
+    assert abs(hh / exact - 1.0) < 1e-8
+
+
 WORKER = r'''
 import os, sys
 sys.path.insert(0, os.environ["TNML_ROOT"])

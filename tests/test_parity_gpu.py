@@ -276,6 +276,50 @@ def test_fixedL_binary_matches_capi(capi, tmp_path):
     h.close()
 
 
+def test_fixedL_cold_start_matches_oracle(capi, tmp_path):
+    """Cold start of the drop-in program (no `W` file): the initial W is the reference's sum of
+    product states (fixedL.cc:702-728); the cost before DMRG and the first bond
+    updates equal the oracle's from the W the program wrote."""
+    import os
+    import re
+    import subprocess
+    from tnml_b200 import data as D
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    binp = os.path.join(root, "tnml_b200", "host", "fixedL")
+    if not os.path.exists(binp):
+        pytest.skip("host binary not built")
+    side = 6
+    N = side * side
+    pix, labels = D.synthetic_digits(200, side, seed=21)
+    u8 = (pix * 255).round().astype(np.uint8)
+    D.write_idx_files(str(tmp_path / "d"), u8, labels, side)
+    base = (f"datadir = {tmp_path}/d\nNtrain = 20\nimglen = {side}\nNbatch = 4\nmaxm = 8\nminm = 4\ncutoff = 1E-10\n"
+            f"Nsweep = 1\nNpass = 3\nninitial = 6\nseed = 3\n")
+    (tmp_path / "in0").write_text("input\n{\n" + base + "init_only = yes\n}\n")
+    r0 = subprocess.run([binp, "in0"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r0.returncode == 0, r0.stderr[-2000:]
+    W0 = D.read_mps_file(str(tmp_path / "W"))          # the initial W, before training overwrites it
+    os.remove(tmp_path / "W")
+    (tmp_path / "in").write_text("input\n{\n" + base + "}\n")
+    r = subprocess.run([binp, "in"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Summing all 10 label states together" in r.stdout
+    c0 = float(re.search(r"Before starting DMRG Cost = ([0-9.eE+-]+)", r.stdout).group(1))
+    costs = [float(x) for x in re.findall(r"--> After SVD, Cost = ([0-9.eE+-]+)", r.stdout)]
+    assert len(costs) == 2 * (N - 1)
+    feat = D.phi(u8.astype(np.float64) / 255.0)
+    lab = labels.astype(np.int64)
+    ts = O.TrainStates(feat, lab)
+    Wc = [None if w is None else w.copy() for w in W0]
+    ts.init(Wc)
+    C, _, _ = O.quadcost(O.form_bond(Wc[1], Wc[2]), ts, detail=True)
+    assert abs(C / 200 - c0) < 2e-10 + 1e-9 * c0
+    ref = O.mldmrg(Wc, ts, 1, 8, 4, 1e-10, Npass=3, max_bonds=6)
+    for k in range(6):
+        assert abs(ref[k]["cost"] - costs[k]) < 2e-10 + 1e-6 * costs[k], (k, ref[k]["cost"], costs[k])
+    assert costs[-1] < c0                                # training reduced the cost
+
+
 @pytest.mark.parametrize("b,ha", [(6, 1), (7, 1), (8, 1), (8, 2), (7, 2), (10, 2)])
 def test_svd_qr_preconditioned_path(capi, b, ha):
     """Larger bond matrices (>= 32 columns) go through Householder QR + Jacobi on R^T

@@ -197,6 +197,30 @@ def write_mps_file(path, W, d=2):
             f.write(struct.pack("<q", A.size) + A.tobytes())
 
 
+def _r_index(f):
+    idx_id, m, n = struct.unpack("<qqq", f.read(24))
+    name = f.read(n).decode()
+    (tn,) = struct.unpack("<q", f.read(8))
+    typ = f.read(tn).decode()
+    return idx_id, m, name, typ
+
+
+def read_mps_file(path):
+    """Read a `W` file written by the fixedL program (TNMLW1): returns the 1-indexed list of site
+    tensors [ml,d,mr] (label site [ml,d,mr,NL])."""
+    with open(path, "rb") as f:
+        if f.read(8)[:6] != b"TNMLW1":
+            raise ValueError(f"not a tnml_b200 MPS file: {path}")
+        (N,) = struct.unpack("<q", f.read(8))
+        W = [None]
+        for _ in range(N):
+            (r,) = struct.unpack("<q", f.read(8))
+            dims = [_r_index(f)[1] for _ in range(r)]
+            (n,) = struct.unpack("<q", f.read(8))
+            W.append(np.frombuffer(f.read(8 * n), np.float64).reshape(dims).copy())
+    return W
+
+
 def write_idx_files(datadir, pix_u8, labels, side, kind="train"):
     """MNIST-format idx3/idx1 files (for running the fixedL binary on synthetic data)."""
     os.makedirs(datadir, exist_ok=True)

@@ -8,8 +8,11 @@
 // Deliberate differences (all logged at start-up):
 //   * `imglen` is honoured (2x2 block mean, image.h:316-346); the reference parses
 //     nothing of the sort and always runs 28x28.  Default 28.
-//   * the initial W is a SEEDED random MPS (`seed`, `minitial` keys) instead of the
-//     time-seeded sum of product states (fixedL.cc:702-728).
+//   * the initial W is built like the reference (sum of `ninitial` random product states per
+//     label, fixedL.cc:702-728, or the W0..W9 merge, 682-701) but the random picks come from a
+//     SEEDED generator (`seed` key; seed < 0 = time-seeded like ITensor's Global::random(),
+//     SURVEY F7).  `initial = random` selects a seeded random MPS of bond dimension `minitial`
+//     instead; `init_only = yes` stops after writing `W` (no GPU needed).
 //   * `W` / `sites` files use this program's own binary format.
 //   * nthread/Nbatch are accepted and validated like the reference but the
 //     parallelism is GPUs: one process per GPU (TNML_RANK / TNML_WORLD_SIZE),
@@ -24,6 +27,7 @@
 
 #include "../../include/tnml_b200.h"
 #include "itensor_lite.h"
+#include "initial_w.h"
 #include "mnist.h"
 
 using namespace itensor;
@@ -424,7 +428,8 @@ int main(int argc, const char* argv[]) {
     auto minitial = input.getInt("minitial", 10);
     auto device = input.getInt("device", -1);
     auto dorel = input.getYesNo("dorelcutoff", false);
-    (void)ninitial;
+    auto initial = input.getString("initial", "sum");
+    auto init_only = input.getYesNo("init_only", false);
 
     int rank = std::getenv("TNML_RANK") ? atoi(std::getenv("TNML_RANK")) : 0;
     int world = std::getenv("TNML_WORLD_SIZE") ? atoi(std::getenv("TNML_WORLD_SIZE")) : 1;
@@ -464,11 +469,10 @@ int main(int argc, const char* argv[]) {
     int totNtrain = (int)states.size();
     printfln("Total of %d training images", totNtrain);
 
-    auto ts = TrainStates(std::move(states), N, sites, Nthread, Nbatch, device, rank, world);
-    printfln("%s", tnml_version());
-
     Index L;
     MPS W;
+    vector<Index> wlinks;
+    bool have_links = false;
     if (fileExists("W")) {
       println("Reading W from disk");
       W = readFromFile<MPS>("W", sites);
@@ -477,19 +481,62 @@ int main(int argc, const char* argv[]) {
         printfln("Expected W to have Label type Index at site %d", c);
         return 1;
       }
-      ts.links.assign(N + 1, Index());
-      for (int j = 1; j <= N; ++j) {
-        auto const& is = W.A(j).inds();
-        ts.links[j - 1] = is.at(0);
-        ts.links[j] = is.at(2);
-      }
-    } else {
+    } else if (fileExists("W0")) {
+      // fixedL.cc:682-701
+      println("Found separate W0,W1,...,W9 MPS: summing");
       L = Index("L", 10, Label);
-      printfln("Making initial W: seeded random MPS (seed=%d, m=%d), label on site %d", seed, minitial, c);
-      W = randomMPS(sites, ts.links, L, c, minitial, (uint64_t)seed);
+      vector<initw::RMPS> ipsis;
+      for (int n = 0; n < (int)NL; ++n) {
+        auto in = initw::from_mps(readFromFile<MPS>(format("W%d", n), sites));
+        initw::tag_label(in, c, n, (int)NL, 1.0);
+        ipsis.push_back(std::move(in));
+      }
+      printfln("Summing all %d label states together", (int)ipsis.size());
+      auto R = initw::sum(ipsis, 1E-10, 1000000, dorel);
+      W = initw::to_mps(R, sites, wlinks, L, c);
+      have_links = true;
       println("Done making initial W");
       if (rank == 0) writeToFile("W", W);
+    } else if (initial == "random") {
+      L = Index("L", 10, Label);
+      printfln("Making initial W: seeded random MPS (seed=%d, m=%d), label on site %d", seed, minitial, c);
+      W = randomMPS(sites, wlinks, L, c, minitial, (uint64_t)seed);
+      have_links = true;
+      println("Done making initial W");
+      if (rank == 0) writeToFile("W", W);
+    } else {
+      // fixedL.cc:702-728: make initial W by summing training states together
+      L = Index("L", 10, Label);
+      Rng rng(seed < 0 ? (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count() : (uint64_t)seed);
+      vector<vector<long>> picks;
+      auto R = initw::initial_sum(N, d, c, (int)NL, train, phi, ninitial, [&rng]() { return rng.uniform(); }, dorel,
+                                  &picks);
+      for (int n = 0; n < (int)NL; ++n) {   // which images were drawn (positions in the training set)
+        string line = format("  label %d picks:", n);
+        for (long w : picks[n]) line += format(" %ld", w);
+        println(line);
+      }
+      W = initw::to_mps(R, sites, wlinks, L, c);
+      have_links = true;
+      println("Done making initial W");
+      if (rank == 0) writeToFile("W", W);
+      printfln("overlap(W,W) = %.12f", initw::overlap(R, R));
     }
+    if (!have_links) {
+      wlinks.assign(N + 1, Index());
+      for (int j = 1; j <= N; ++j) {
+        auto const& is = W.A(j).inds();
+        wlinks[j - 1] = is.at(0);
+        wlinks[j] = is.at(2);
+      }
+    }
+    println("Done making initial W");
+    if (!findtype(W.A(c), Label)) Error(format("Label Index not on site %d", c));
+    if (init_only) return 0;
+
+    auto ts = TrainStates(std::move(states), N, sites, Nthread, Nbatch, device, rank, world);
+    printfln("%s", tnml_version());
+    ts.links = wlinks;
     ts.L = L;
     train.clear();  // to save memory
     if (!findtype(W.A(c), Label)) Error(format("Label Index not on site %d", c));
