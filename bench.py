@@ -52,27 +52,64 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons during the timed region: NVML (nvidia_ml_py, ~1 ms per sample),
+    falling back to nvidia-smi (the recipe's clocks line)."""
 
-    def __init__(self, gpu_index):
-        self.rows = []
+    def __init__(self, gpu_index, uuid=None):
+        self.rows = []          # (sm_mhz, sm_max_mhz, [reasons])
         self.stop = False
         self.idx = gpu_index
+        self.uuid = uuid
         self.t = None
+        self.how = None
 
-    def _run(self):
+    def _run_nvml(self):
+        import pynvml as N
+        N.nvmlInit()
+        try:
+            h = N.nvmlDeviceGetHandleByUUID(self.uuid) if self.uuid else N.nvmlDeviceGetHandleByIndex(self.idx)
+        except Exception:
+            h = N.nvmlDeviceGetHandleByIndex(self.idx)
+        mx = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": N.nvmlClocksEventReasonHwSlowdown if hasattr(N, "nvmlClocksEventReasonHwSlowdown")
+                else N.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": getattr(N, "nvmlClocksEventReasonHwThermalSlowdown",
+                                               getattr(N, "nvmlClocksThrottleReasonHwThermalSlowdown", 0)),
+                "sw_thermal_slowdown": getattr(N, "nvmlClocksEventReasonSwThermalSlowdown",
+                                               getattr(N, "nvmlClocksThrottleReasonSwThermalSlowdown", 0)),
+                "sw_power_cap": getattr(N, "nvmlClocksEventReasonSwPowerCap",
+                                        getattr(N, "nvmlClocksThrottleReasonSwPowerCap", 0))}
+        get = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.how = "nvml"
+        while not self.stop:
+            sm = float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
+            r = int(get(h))
+            self.rows.append((sm, mx, [k for k, b in bits.items() if b and (r & b)]))
+            time.sleep(0.005)
+        N.nvmlShutdown()
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self.how = "nvidia-smi"
         while not self.stop:
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 f = [x.strip() for x in out.strip().split(",")]
                 if len(f) >= 6:
-                    self.rows.append(f)
+                    self.rows.append((float(f[0]), float(f[1]),
+                                      [n for i, n in enumerate(names) if f[2 + i].lower().startswith("active")]))
             except Exception:
                 pass
             time.sleep(0.05)
+
+    def _run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
 
     def start(self):
         self.t = threading.Thread(target=self._run, daemon=True)
@@ -84,11 +121,10 @@ class ClockSampler:
             self.t.join(timeout=6)
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted({x for r in self.rows for x in r[2]})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": reasons,
+                "samples": len(self.rows), "how": self.how}
 
 
 def build_workload(args, rank, world):
@@ -209,7 +245,29 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(nsteps, b_start, e2e=False):
+    # Bond schedule: class-L bonds with m_l = m_r = maxm only, b = first_bond .. jc-2 going right,
+    # then bouncing inside that range like sweepnext does at the chain ends (the turning bond is
+    # optimised twice in a row, fixedL.cc:470-476) so that any --steps K can be served.
+    lo, hi = b0, 196 // 2 - 2
+
+    def schedule():
+        b, ha = lo, 1
+        while True:
+            yield b, ha
+            if ha == 1:
+                if b == hi:
+                    ha = 2
+                else:
+                    b += 1
+            else:
+                if b == lo:
+                    ha = 1
+                else:
+                    b -= 1
+    sched = schedule()
+    visited = []
+
+    def timed(nsteps, e2e=False):
         """K bond updates; device time by CUDA events on the library's stream."""
         res = []
         h2d = d2h = 0
@@ -218,12 +276,14 @@ def run_ours(args):
         with torch.cuda.stream(ext):
             ev0.record()
         for k in range(nsteps):
-            b = b_start + k
+            b, ha = next(sched)
+            visited.append(b)
             if e2e:   # the host owns the MPS (like the reference's `W`): sites go H2D, results D2H
                 for j in (b, b + 1):
-                    h.set_site(j, Whost[j])
-                    h2d += Whost[j].nbytes
-            r = h.bond_update(b, 1, p)
+                    Wj = h.get_site(j) if Whost.get(j) is None else Whost[j]
+                    h.set_site(j, Wj)
+                    h2d += Wj.nbytes
+            r = h.bond_update(b, ha, p)
             if e2e:
                 for j in (b, b + 1):
                     Whost[j] = h.get_site(j)
@@ -241,36 +301,40 @@ def run_ours(args):
         return ms, res, h2d, d2h
 
     K, Wm = args.steps, max(args.warmup, 3)
-    ms, _, _, _ = timed(Wm, b0)                       # warm-up
-    b = b0 + Wm
-    sampler = ClockSampler(local)
+    Whost = {}
+    ms, _, _, _ = timed(Wm)                           # warm-up
+    uuid = None
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        pass
+    sampler = ClockSampler(local, uuid)
     if rank == 0:
         sampler.start()
     h.stats(reset=True)
-    ms, res, _, _ = timed(K, b)
+    ms, res, _, _ = timed(K)
     st = h.stats(reset=True)
     clocks = sampler.finish() if rank == 0 else None
-    b += K
     value = K / (ms / 1000.0)
+    timed_bonds = visited[Wm:Wm + K]
 
     # breakdown pass with per-phase CUDA events (on the library's stream)
     h.set_timing(True)
-    ms_t, res_t, _, _ = timed(K, b)
+    ms_t, res_t, _, _ = timed(K)
     stt = h.stats(reset=True)
     h.set_timing(False)
-    b += K
 
-    # end-to-end pass: host-resident MPS, site tensors cross PCIe every step
-    Whost = {j: None for j in range(1, 197)}
-    for j in range(b, b + K + 2):
+    # end-to-end pass: host-resident MPS, site tensors cross PCIe every step.  The host copies of
+    # the sites the pass will touch are fetched before the timed region (they are inputs).
+    for j in range(lo, hi + 2):
         Whost[j] = h.get_site(j)
-    ms_e, res_e, h2d, d2h = timed(K, b, e2e=True)
+    ms_e, res_e, h2d, d2h = timed(K, e2e=True)
     e2e_value = K / (ms_e / 1000.0)
 
     value_reuse = None
-    if not args.cg_reuse_forward and b + K + 2 < 96:
+    if not args.cg_reuse_forward:
         h.set_option("cg_reuse_forward", 1)
-        ms_r, _, _, _ = timed(K, b + K)
+        ms_r, _, _, _ = timed(K)
         h.set_option("cg_reuse_forward", 0)
         value_reuse = K / (ms_r / 1000.0)
 
@@ -330,7 +394,8 @@ def run_ours(args):
                 "gpu_launches": int(st.launches), "clocks": clocks, "roofline": roof, "roofline_hbm": roof_hbm,
                 "svd": svd_info,
                 "value_cg_reuse_forward": value_reuse,
-                "setup_s": setup_s, "newm": [int(r.newm) for r in res][:8],
+                "setup_s": setup_s, "newm": [int(r.newm) for r in res][:8], "newm_min": min(int(r.newm) for r in res),
+                "timed_bonds": [int(timed_bonds[0]), int(timed_bonds[-1])],
                 "cost_per_image": [r.cost / NTg for r in res][:4]}
         if not args.no_cpu_baseline:
             base, _ = cpu_baseline(args, steps=1)

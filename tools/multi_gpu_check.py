@@ -44,13 +44,20 @@ def main():
         ref.set_mps(W)
         ref.init_envs()
         worst, early = 0.0, 0.0
+        mism = []
         for k, (bb, ha) in enumerate(sched):
             r = ref.bond_update(bb, ha, p)
             e = abs(r.cost - mine[k].cost) / r.cost
             worst = max(worst, e)
             if k < 4:
                 early = max(early, e)
-            if r.newm != mine[k].newm or abs(r.ncorrect - mine[k].ncorrect) > NT // 100:
+            if r.newm != mine[k].newm:
+                # a singular value sitting at the cutoff can fall on either side once the
+                # trajectories have drifted apart; in the first bonds it must not
+                mism.append((k, r.newm, mine[k].newm))
+                if k < 4 or abs(r.newm - mine[k].newm) > 2:
+                    ok = False
+            if abs(r.ncorrect - mine[k].ncorrect) > NT // 100:
                 ok = False
         # The all-reduce only changes the summation order (1e-16).  The first bonds must
         # therefore agree to ~1e-10; later the algorithm itself amplifies that noise by up to
@@ -58,7 +65,7 @@ def main():
         # ParallelDo shard counts do, so only a loose bound is meaningful there.
         ok = ok and early < 1e-9 and worst < 5e-2
         print(f"multi_gpu_check world={world}: rel cost deviation vs single rank: first 4 bonds {early:.2e}, "
-              f"whole sweep {worst:.2e} -> {'OK' if ok else 'FAIL'}")
+              f"whole sweep {worst:.2e}; newm differs at {mism} -> {'OK' if ok else 'FAIL'}")
         ref.close()
     # every rank must hold the same MPS (SVD runs replicated on bit-identical all-reduced data)
     Wm = np.concatenate([h.get_site(j).ravel() for j in range(1, N + 1)])
