@@ -172,7 +172,13 @@ int tnml_comm_init_rank(tnml_handle h, int nranks, int rank, const uint8_t* id);
  * linearly, P(B + a p) = P(B) + a P(p) with P(p) taken from the pAp pass (fixedL.cc:393-402), and
  * only the backward half is re-evaluated -- same mathematics, 3 of 13 projection passes fewer.
  * "reserve_m": environment slots are allocated for this link dimension so that they never have to
- * grow during the sweeps (tnml_bond_update raises it to maxm by itself). */
+ * grow during the sweeps (tnml_bond_update raises it to maxm by itself).
+ * "env_budget_gb" (default 0 = keep everything in HBM): environment tiering.  The reference keeps
+ * every per-image environment on disk (proj_images/, fixedL.cc:153,231) and reads the two a bond
+ * needs (fixedL.cc:177-178); here at most this many GiB of environment slots stay in HBM, the rest
+ * lives in pinned host memory.  Slots are evicted farthest-next-use first and the slot the next
+ * bond needs is fetched on a copy stream while the current bond computes.  Results are bit-identical
+ * to the all-resident run. */
 int tnml_set_option(tnml_handle h, const char* name, double value);
 
 /* Counters for the roofline report: kernel launches issued by this library,
@@ -182,6 +188,8 @@ typedef struct tnml_stats {
   double alg_bytes;
   double alg_flops;
   double ms_proj, ms_grad, ms_fat, ms_svd, ms_shift, ms_other; /* if timing on */
+  int64_t tier_evictions, tier_fetches;  /* environment slots moved HBM -> host / host -> HBM */
+  double tier_bytes;                     /* bytes that crossed PCIe for the environment tier */
 } tnml_stats;
 int tnml_get_stats(tnml_handle h, tnml_stats* out, int reset);
 int tnml_set_timing(tnml_handle h, int on); /* CUDA-event timing of each phase */

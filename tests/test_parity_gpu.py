@@ -276,6 +276,49 @@ def test_fixedL_binary_matches_capi(capi, tmp_path):
     h.close()
 
 
+def test_env_tier_bit_identical(capi):
+    """environment tiering.  With an HBM budget that holds only a handful of
+    environment slots (the rest live in pinned host memory, fetched ahead on a copy stream) two
+    sweeps produce bit-identical costs, link dims and MPS as the all-resident run; the tier really
+    moved data; an evicted slot can still be read back and equals the oracle's."""
+    feat, labels, W = make_problem(N=16, NT=256, m0=4)
+    p = capi.BondParams(3, 0.0, 1e-10, 1e-10, 8, 4, 0)
+    runs = []
+    for budget_gb in (0.0, 0.0012):      # 0.0012 GiB = 1.29 MB: ~7 label-carrying slots of 256x10x8 doubles
+        h = capi.Handle(0)
+        h.set_images(feat, labels.astype(np.int32))
+        h.set_mps(W)
+        if budget_gb:
+            h.set_option("env_budget_gb", budget_gb)
+        h.init_envs()
+        h.stats(reset=True)
+        out = []
+        for sw in range(2):
+            for b, ha in O.sweep_schedule(16):
+                r = h.bond_update(b, ha, p)
+                out.append((r.cost, r.newm, r.ncorrect, r.truncerr))
+        st = h.stats(reset=True)
+        mps = [h.get_site(j) for j in range(1, 17)]
+        envs = {}
+        for j in (1, 5, 9, 14):           # left envs far behind the last bond (bond 1, moving left): some evicted
+            try:
+                envs[j] = h.get_env(j)
+            except capi.TnmlError:
+                envs[j] = None
+        runs.append((out, mps, st, envs))
+        h.close()
+    (o0, m0, s0, e0), (o1, m1, s1, e1) = runs
+    assert o0 == o1                                           # bit-identical, not just close
+    assert all(np.array_equal(a, b) for a, b in zip(m0, m1))
+    assert s0.tier_evictions == 0 and s0.tier_fetches == 0
+    assert s1.tier_evictions > 10 and s1.tier_fetches > 10 and s1.tier_bytes > 0
+    for j in e0:
+        if e0[j] is None:
+            assert e1[j] is None
+        else:
+            assert np.array_equal(e0[j], e1[j])
+
+
 def test_fixedL_cold_start_matches_oracle(capi, tmp_path):
     """Cold start of the drop-in program (no `W` file): the initial W is the reference's sum of
     product states (fixedL.cc:702-728); the cost before DMRG and the first bond

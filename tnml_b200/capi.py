@@ -45,7 +45,8 @@ class BondResult(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("launches", C.c_int64), ("alg_bytes", C.c_double), ("alg_flops", C.c_double),
                 ("ms_proj", C.c_double), ("ms_grad", C.c_double), ("ms_fat", C.c_double),
-                ("ms_svd", C.c_double), ("ms_shift", C.c_double), ("ms_other", C.c_double)]
+                ("ms_svd", C.c_double), ("ms_shift", C.c_double), ("ms_other", C.c_double),
+                ("tier_evictions", C.c_int64), ("tier_fetches", C.c_int64), ("tier_bytes", C.c_double)]
 
 
 # every symbol include/tnml_b200.h declares (tests check the library exports all)

@@ -22,11 +22,19 @@ namespace {
 std::string g_err;  // create-time errors
 
 struct Slot {
-  double* p = nullptr;
-  size_t bytes = 0;
+  double* p = nullptr;   // device copy (nullptr: not resident)
+  size_t bytes = 0;      // capacity of the device buffer
   int m = 0;
   int fat = 0;
   int kind = 0;  // 0 empty, 1 left env, 2 right env
+  // host tier (the reference keeps every environment in proj_images/ and reads two
+  // per bond, fixedL.cc:177-178,231): pinned copy, valid iff host_valid
+  double* host = nullptr;
+  size_t host_bytes = 0;
+  bool host_valid = false;
+  cudaEvent_t ready = nullptr;   // recorded on the fetch stream after an H2D fetch
+  bool pending = false;          // the main stream has not waited for `ready` yet
+  cudaEvent_t saved = nullptr;   // recorded on the eviction stream after the D2H write-back
 };
 struct Site {
   double* d = nullptr;
@@ -112,6 +120,12 @@ struct tnml_handle_s {
   double* PV = nullptr; // [NT][NL]  p*v_n of the current CG pass (cg_reuse_forward)
   int cg_reuse_forward = 0;
   int reserve_m = 0;       // env slots are sized for this link dim (set from maxm by tnml_bond_update)
+  // environment tiering: at most env_budget bytes of slots resident in HBM (0 = everything)
+  cudaStream_t cp = nullptr;     // eviction stream (D2H) -- copies overlap the kernels and each other
+  cudaStream_t cpin = nullptr;   // fetch stream (H2D)
+  cudaEvent_t ev_main = nullptr;
+  size_t env_budget = 0, env_resident = 0;
+  int moving = 1;                // 1: sweeping right (Fromleft), 2: sweeping left
   int32_t* pred = nullptr;
   double* stats_partial = nullptr;
   int nfat_blocks = 0;
@@ -219,6 +233,111 @@ void drain_events(tnml_handle h) {
 
 const double* featp(tnml_handle h, int j) { return h->feat + (long)j * h->NT * 2; }
 
+// ---- environment tier ---------------------------------------------------------------------------
+size_t slot_used(tnml_handle h, const Slot& s) { return (size_t)h->NT * s.m * (s.fat ? NL : 1) * sizeof(double); }
+
+// make the main stream wait for an in-flight fetch of this slot
+int use_slot(tnml_handle h, Slot& s) {
+  if (s.pending) {
+    CK(cudaStreamWaitEvent(h->st, s.ready, 0));
+    s.pending = false;
+  }
+  return 0;
+}
+
+int free_slot_dev(tnml_handle h, Slot& s, cudaStream_t on) {
+  if (!s.p) return 0;
+  CK(cudaFreeAsync(s.p, on));
+  h->env_resident -= s.bytes;
+  s.p = nullptr;
+  s.bytes = 0;
+  return 0;
+}
+
+// write the slot back to pinned host memory (if the host copy is stale) and release the device copy
+int evict_slot(tnml_handle h, Slot& s) {
+  if (!s.p) return 0;
+  TRY(use_slot(h, s));
+  CK(cudaEventRecord(h->ev_main, h->st));          // everything queued so far may still read it
+  CK(cudaStreamWaitEvent(h->cp, h->ev_main, 0));
+  const size_t used = slot_used(h, s);
+  if (!s.host_valid) {
+    if (s.host_bytes < used) {
+      // pinning host memory runs at only 1-2 GB/s (measured), so the buffer is sized for the
+      // largest link dimension the slot can reach and allocated once
+      const size_t want = std::max(used, (size_t)h->NT * std::max(s.m, h->reserve_m) * (s.fat ? NL : 1) * sizeof(double));
+      if (s.host) CK(cudaFreeHost(s.host));
+      s.host = nullptr;
+      s.host_bytes = 0;
+      if (cudaMallocHost(&s.host, want) != cudaSuccess) {
+        cudaGetLastError();
+        CK(cudaMallocHost(&s.host, used));
+        s.host_bytes = used;
+      } else {
+        s.host_bytes = want;
+      }
+    }
+    CK(cudaMemcpyAsync(s.host, s.p, used, cudaMemcpyDeviceToHost, h->cp));
+    if (!s.saved) CK(cudaEventCreateWithFlags(&s.saved, cudaEventDisableTiming));
+    CK(cudaEventRecord(s.saved, h->cp));
+    s.host_valid = true;
+    h->stats.tier_bytes += (double)used;
+  }
+  h->stats.tier_evictions += 1;
+  return free_slot_dev(h, s, h->cp);
+}
+
+// The slot whose next use lies farthest in the future: moving right at bond b the left
+// environments behind us (small j) are needed again only on the way back, lowest j last; the right
+// environments ahead are needed soon, highest j last.  Mirror image when moving left.
+int pick_victim(tnml_handle h, int lo_keep, int hi_keep) {
+  const int N = h->N;
+  if (h->moving == 1) {
+    for (int j = 1; j < lo_keep; ++j)
+      if (h->slot[j].p) return j;
+    for (int j = N; j > hi_keep; --j)
+      if (h->slot[j].p) return j;
+  } else {
+    for (int j = N; j > hi_keep; --j)
+      if (h->slot[j].p) return j;
+    for (int j = 1; j < lo_keep; ++j)
+      if (h->slot[j].p) return j;
+  }
+  return -1;
+}
+
+// evict until `need` more bytes fit under the budget; slots lo_keep..hi_keep are protected
+int make_room(tnml_handle h, size_t need, int lo_keep, int hi_keep) {
+  if (h->env_budget == 0) return 0;
+  while (h->env_resident + need > h->env_budget) {
+    const int v = pick_victim(h, lo_keep, hi_keep);
+    if (v < 0) break;   // only protected slots left: exceed the budget rather than fail
+    TRY(evict_slot(h, h->slot[v]));
+  }
+  return 0;
+}
+
+// bring slot j back to HBM on the copy stream (no-op if resident or empty)
+int fetch_slot(tnml_handle h, int j, int lo_keep, int hi_keep) {
+  if (j < 1 || j > h->N) return 0;
+  Slot& s = h->slot[j];
+  if (s.kind == 0 || s.p) return 0;
+  if (!s.host_valid) return fail(h, TNML_ERR_INVALID, "environment slot %d lost (neither in HBM nor on the host)", j);
+  const size_t used = slot_used(h, s);
+  TRY(make_room(h, used, lo_keep, hi_keep));
+  CK(cudaMallocAsync(&s.p, used, h->cpin));
+  s.bytes = used;
+  h->env_resident += used;
+  if (s.saved) CK(cudaStreamWaitEvent(h->cpin, s.saved, 0));   // the write-back of this slot has landed
+  CK(cudaMemcpyAsync(s.p, s.host, used, cudaMemcpyHostToDevice, h->cpin));
+  if (!s.ready) CK(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+  CK(cudaEventRecord(s.ready, h->cpin));
+  s.pending = true;
+  h->stats.tier_fetches += 1;
+  h->stats.tier_bytes += (double)used;
+  return 0;
+}
+
 // env accessors for bond b: returns pointer, dim, fat flag
 struct EnvRef {
   const double* p;
@@ -232,6 +351,8 @@ int left_env(tnml_handle h, int b, EnvRef& e) {
   }
   Slot& s = h->slot[b - 1];
   if (s.kind != 1) return fail(h, TNML_ERR_INVALID, "left environment slot %d not built (kind=%d)", b - 1, s.kind);
+  TRY(fetch_slot(h, b - 1, b - 1, b + 2));
+  TRY(use_slot(h, s));
   e = {s.p, s.m, s.fat};
   return 0;
 }
@@ -242,6 +363,8 @@ int right_env(tnml_handle h, int b, EnvRef& e) {
   }
   Slot& s = h->slot[b + 2];
   if (s.kind != 2) return fail(h, TNML_ERR_INVALID, "right environment slot %d not built (kind=%d)", b + 2, s.kind);
+  TRY(fetch_slot(h, b + 2, b - 1, b + 2));
+  TRY(use_slot(h, s));
   e = {s.p, s.m, s.fat};
   return 0;
 }
@@ -456,16 +579,18 @@ int ddot(tnml_handle h, long n, const double* x, const double* y, double* out) {
 // grow towards maxm; growing a slot means a fresh cudaMallocAsync of up to 0.6 GB (measured:
 // 20 ms stalls on ~1 bond in 10 during the first sweeps), so slots are sized for maxm at once
 // while that fits comfortably in HBM.
-int alloc_slot(tnml_handle h, Slot& s, size_t bytes, size_t reserve) {
+int alloc_slot(tnml_handle h, Slot& s, size_t bytes, size_t reserve, int lo_keep, int hi_keep) {
+  TRY(use_slot(h, s));
   if (s.p && s.bytes >= bytes) return 0;
-  if (s.p) CK(cudaFreeAsync(s.p, h->st));
-  s.p = nullptr;
-  s.bytes = 0;
+  TRY(free_slot_dev(h, s, h->st));
+  if (h->env_budget) reserve = bytes;   // tiering: exact sizes, the budget is what matters
+  TRY(make_room(h, bytes, lo_keep, hi_keep));
   if (reserve > bytes) {
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && fr > reserve + (tot >> 3) &&
         cudaMallocAsync(&s.p, reserve, h->st) == cudaSuccess) {
       s.bytes = reserve;
+      h->env_resident += reserve;
       return 0;
     }
     cudaGetLastError();
@@ -473,6 +598,7 @@ int alloc_slot(tnml_handle h, Slot& s, size_t bytes, size_t reserve) {
   }
   CK(cudaMallocAsync(&s.p, bytes, h->st));
   s.bytes = bytes;
+  h->env_resident += bytes;
   return 0;
 }
 
@@ -485,11 +611,14 @@ int advance_env(tnml_handle h, int c, int right) {
   const int prevc = right ? c + 1 : c - 1;
   const bool hasPrev = (prevc >= 1 && prevc <= h->N);
   EnvRef pe{h->ones, 1, 0};
+  const int klo = std::min(c, prevc), khi = std::max(c, prevc);   // slots this call touches
   if (hasPrev) {
     Slot& ps = h->slot[prevc];
     if (ps.kind != (right ? 2 : 1))
       return fail(h, TNML_ERR_INVALID, "cannot advance env to site %d: slot %d not a %s env", c, prevc,
                   right ? "right" : "left");
+    TRY(fetch_slot(h, prevc, klo, khi));
+    TRY(use_slot(h, ps));
     pe = {ps.p, ps.m, ps.fat};
   }
   const int kin = right ? w.mr : w.ml;    // contracted link
@@ -500,7 +629,8 @@ int advance_env(tnml_handle h, int c, int right) {
   Slot& ns = h->slot[c];
   const size_t bytes = (size_t)NT * kout * (outfat ? NL : 1) * sizeof(double);
   const size_t reserve = (size_t)NT * std::max(kout, h->reserve_m) * (outfat ? NL : 1) * sizeof(double);
-  TRY(alloc_slot(h, ns, bytes, reserve));
+  TRY(alloc_slot(h, ns, bytes, reserve, klo, khi));
+  ns.host_valid = false;   // about to be overwritten
   const double* Bm = w.d;
   PhaseTimer t(h, PH_SHIFT);
   if (right || w.lab) {
@@ -567,7 +697,10 @@ int tnml_create(int device, int flags, tnml_handle* out) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   h->num_sm = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->cp, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->cpin, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming) != cudaSuccess) {
     delete h;
     return fail(nullptr, TNML_ERR_CUDA, "cudaStreamCreate failed");
   }
@@ -593,8 +726,14 @@ int tnml_destroy(tnml_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->st);
   if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
-  for (auto& s : h->slot)
+  if (h->cp) cudaStreamSynchronize(h->cp);
+  if (h->cpin) cudaStreamSynchronize(h->cpin);
+  for (auto& s : h->slot) {
     if (s.p) cudaFree(s.p);
+    if (s.host) cudaFreeHost(s.host);
+    if (s.ready) cudaEventDestroy(s.ready);
+    if (s.saved) cudaEventDestroy(s.saved);
+  }
   for (auto& s : h->W)
     if (s.d) cudaFree(s.d);
   DBuf* bufs[] = {&h->B, &h->r, &h->p, &h->G, &h->T, &h->Gpart, &h->Q, &h->Z, &h->Bm};
@@ -612,6 +751,9 @@ int tnml_destroy(tnml_handle h) {
     cudaEventDestroy(e.b);
   }
   for (auto e : h->evpool) cudaEventDestroy(e);
+  if (h->ev_main) cudaEventDestroy(h->ev_main);
+  if (h->cp) cudaStreamDestroy(h->cp);
+  if (h->cpin) cudaStreamDestroy(h->cpin);
   cudaStreamDestroy(h->st);
   delete h;
   return TNML_OK;
@@ -625,8 +767,15 @@ int tnml_set_images(tnml_handle h, int64_t NT, int N, const double* feat, const 
     if (labels[n] < 0 || labels[n] >= NL) return fail(h, TNML_ERR_INVALID, "label %d of image %ld out of range", labels[n], (long)n);
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->st));
-  for (auto& s : h->slot)
+  CK(cudaStreamSynchronize(h->cp));
+  CK(cudaStreamSynchronize(h->cpin));
+  for (auto& s : h->slot) {
     if (s.p) cudaFree(s.p);
+    if (s.host) cudaFreeHost(s.host);
+    if (s.ready) cudaEventDestroy(s.ready);
+    if (s.saved) cudaEventDestroy(s.saved);
+  }
+  h->env_resident = 0;
   for (auto& s : h->W)
     if (s.d) cudaFree(s.d);
   void* ptrs[] = {h->feat, h->labels, h->ones, h->P, h->PV, h->pred};
@@ -703,8 +852,13 @@ int tnml_init_envs(tnml_handle h) {
   for (int j = 1; j <= h->N; ++j)
     if (!h->W[j].d) return fail(h, TNML_ERR_INVALID, "site tensor %d not set", j);
   if (!h->W[h->jc].lab) return fail(h, TNML_ERR_INVALID, "Label Index not on site %d", h->jc);
-  for (auto& s : h->slot) s.kind = 0;
+  for (auto& s : h->slot) {
+    s.kind = 0;
+    s.host_valid = false;
+  }
+  h->moving = 2;   // building right environments N..3: the high slots are needed last
   for (int n = h->N; n >= 3; --n) TRY(advance_env(h, n, 1));
+  h->moving = 1;
   h->currb = -1;
   return tnml_set_bond(h, 1);
 }
@@ -715,6 +869,17 @@ int tnml_set_bond(tnml_handle h, int b) {
   if (h->currb == b) return TNML_OK;  // fixedL.cc:162
   h->currb = b;
   h->bond_valid = false;
+  if (h->env_budget) {
+    // tiering: the two environments of this bond (fixedL.cc:177-178 reads them from disk), then
+    // the one the next bond will need, fetched on the copy stream while this bond computes
+    CK(cudaSetDevice(h->device));
+    TRY(fetch_slot(h, b - 1, b - 1, b + 2));
+    TRY(fetch_slot(h, b + 2, b - 1, b + 2));
+    if (h->moving == 1)
+      TRY(fetch_slot(h, b + 3, b - 1, b + 3));
+    else
+      TRY(fetch_slot(h, b - 2, b - 2, b + 2));
+  }
   return TNML_OK;
 }
 
@@ -920,6 +1085,7 @@ int tnml_shift_env(tnml_handle h, int b, int dir) {
   if (dir != TNML_FROMLEFT && dir != TNML_FROMRIGHT) return fail(h, TNML_ERR_INVALID, "bad direction %d", dir);
   CK(cudaSetDevice(h->device));
   const int c = (dir == TNML_FROMLEFT) ? b : b + 1;  // fixedL.cc:196
+  h->moving = (dir == TNML_FROMLEFT) ? 1 : 2;
   return advance_env(h, c, dir == TNML_FROMLEFT ? 0 : 1);
 }
 
@@ -929,6 +1095,7 @@ int tnml_bond_update(tnml_handle h, int b, int ha, const tnml_bond_params* p, tn
   tnml_bond_result res;
   memset(&res, 0, sizeof(res));
   if (p->maxm > h->reserve_m) h->reserve_m = p->maxm;
+  h->moving = ha;
   TRY(tnml_set_bond(h, b));                                            // 488
   TRY(tnml_bond_form(h));                                              // 493-498
   res.origm = h->W[b].mr;
@@ -983,6 +1150,8 @@ int tnml_get_env(tnml_handle h, int slot, int* m, int* is_fat, double* data, siz
     size_t n = (size_t)h->NT * s.m * (s.fat ? NL : 1);
     if (capacity_elems < n) return fail(h, TNML_ERR_INVALID, "buffer too small for slot %d", slot);
     CK(cudaSetDevice(h->device));
+    TRY(fetch_slot(h, slot, slot, slot));
+    TRY(use_slot(h, s));
     CK(cudaMemcpyAsync(data, s.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
   }
@@ -1022,6 +1191,11 @@ int tnml_set_option(tnml_handle h, const char* name, double value) {
     h->cg_reuse_forward = (value != 0.0);
     return TNML_OK;
   }
+  if (strcmp(name, "env_budget_gb") == 0) {
+    if (value < 0) return fail(h, TNML_ERR_INVALID, "env_budget_gb must be >= 0");
+    h->env_budget = (size_t)(value * 1073741824.0);
+    return TNML_OK;
+  }
   if (strcmp(name, "reserve_m") == 0) {
     h->reserve_m = (int)value;
     return TNML_OK;
@@ -1050,6 +1224,8 @@ int tnml_synchronize(tnml_handle h) {
   if (!h) return TNML_ERR_INVALID;
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->st));
+  CK(cudaStreamSynchronize(h->cp));
+  CK(cudaStreamSynchronize(h->cpin));
   return TNML_OK;
 }
 

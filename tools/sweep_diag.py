@@ -1,6 +1,6 @@
 """Per-bond diagnostics of full sweeps (config 2/3 shapes): link dims, SVD sweeps, wall time per
 bond and the CUDA-event phase breakdown per sweep.  Run on the GPU box:
-  python tools/sweep_diag.py [NT] [maxm] [nsweep]        -> gpurun_out/sweep_diag.txt"""
+  python tools/sweep_diag.py [NT] [maxm] [nsweep] [env_budget_gb]        -> gpurun_out/sweep_diag.txt"""
 import os
 import sys
 import time
@@ -14,6 +14,7 @@ from tnml_b200 import capi, data, fixedl  # noqa: E402
 NT = int(sys.argv[1]) if len(sys.argv) > 1 else 60000
 maxm = int(sys.argv[2]) if len(sys.argv) > 2 else 120
 nsweep = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+budget_gb = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0     # environment tier: HBM budget for env slots
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 out = open(os.path.join(ROOT, "gpurun_out", "sweep_diag.txt"), "a")
 
@@ -29,10 +30,12 @@ pix, labels = data.synthetic_digits(NT, 14, seed=20260925)
 feat = data.phi(pix)
 W = data.random_mps(196, 2, 10, seed=3)
 ts = fixedl.TrainStates(feat, labels)
+if budget_gb:
+    ts.h.set_option("env_budget_gb", budget_gb)
 ts.init(W, reserve_m=maxm)
 h = ts.h
 p = capi.BondParams(4, 0.0, 1e-10, 1e-10, maxm, max(10, maxm // 2), 0)
-say(f"# sweep_diag NT={NT} maxm={maxm} ({capi.load_library().tnml_version().decode()})")
+say(f"# sweep_diag NT={NT} maxm={maxm} env_budget_gb={budget_gb} ({capi.load_library().tnml_version().decode()})")
 for sw in range(1, nsweep + 1):
     h.set_timing(True)
     h.stats(reset=True)
@@ -48,7 +51,8 @@ for sw in range(1, nsweep + 1):
     a = np.array(rows)
     say(f"sweep {sw}: {len(rows)} bonds in {dt:.2f} s = {len(rows) / dt:.1f}/s; phases ms/bond: proj {st.ms_proj / 390:.2f} "
         f"grad {st.ms_grad / 390:.2f} fat {st.ms_fat / 390:.2f} svd {st.ms_svd / 390:.2f} shift {st.ms_shift / 390:.2f} "
-        f"other {st.ms_other / 390:.2f}; launches {st.launches}")
+        f"other {st.ms_other / 390:.2f}; launches {st.launches}; tier: {st.tier_evictions} evictions, {st.tier_fetches} fetches, "
+        f"{st.tier_bytes / 1e9:.1f} GB over PCIe")
     say(f"   newm: min {int(a[:, 3].min())} median {int(np.median(a[:, 3]))} max {int(a[:, 3].max())}; svd sweeps: "
         f"median {int(np.median(a[:, 4]))} max {int(a[:, 4].max())} hist {np.bincount(a[:, 4].astype(int)).tolist()}")
     for k in list(range(0, 390, 15)) + [96, 97, 98, 99, 291, 292, 293]:
