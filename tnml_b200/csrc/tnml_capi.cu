@@ -180,13 +180,22 @@ int fail(tnml_handle h, int code, const char* fmt, ...) {
     if (rc_ != 0) return rc_; \
   } while (0)
 
-int ensure(tnml_handle h, DBuf& b, size_t n) {
+// Work buffers grow with the link dimensions during the first sweeps.  Growing the stream-ordered
+// pool is expensive (measured: 0.3 - 1.4 s stalls on single bonds of an otherwise 5 ms/bond sweep),
+// so a buffer that has to grow is sized for `want` (what it will need at maxm, when known) or at
+// least 1.5x its old capacity.
+int ensure(tnml_handle h, DBuf& b, size_t n, size_t want = 0) {
   if (n <= b.cap) return 0;
+  size_t target = std::max(n, std::max(want, b.cap + b.cap / 2));
   if (b.p) CK(cudaFreeAsync(b.p, h->st));
   b.p = nullptr;
   b.cap = 0;
-  CK(cudaMallocAsync(&b.p, n * sizeof(double), h->st));
-  b.cap = n;
+  if (target > n) {
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess || fr < target * sizeof(double) + (tot >> 3)) target = n;
+  }
+  CK(cudaMallocAsync(&b.p, target * sizeof(double), h->st));
+  b.cap = target;
   return 0;
 }
 
@@ -426,8 +435,9 @@ int forward(tnml_handle h, const double* X, int mode, double* dstats, double* Po
     const double* fth = featp(h, L ? b : b + 1);
     const double* ffa = featp(h, L ? b + 1 : b);
     const int mt = thin.m, mf = fat.m;
-    TRY(ensure(h, h->Q, (size_t)NT * mf));
-    if (mode == FAT_GRAD) TRY(ensure(h, h->Z, (size_t)NT * mf));
+    const size_t wantq = (size_t)NT * std::max(mf, h->reserve_m);
+    TRY(ensure(h, h->Q, (size_t)NT * mf, wantq));
+    if (mode == FAT_GRAD) TRY(ensure(h, h->Z, (size_t)NT * mf, wantq));
     {
       PhaseTimer t(h, PH_PROJ);
       krgemm(h->st, 4, thin.p, mt, mt, fth, ffa, 1, X, mf, mf, h->Q.p, mf, NT, h->num_sm);
@@ -446,8 +456,9 @@ int forward(tnml_handle h, const double* X, int mode, double* dstats, double* Po
     h->stats.alg_bytes += 8.0 * NT * ((double)mt + (double)NL * mf + 4);
   } else {
     const long J = (long)NL * g.mr;
-    TRY(ensure(h, h->Q, (size_t)NT * J));
-    if (mode == FAT_GRAD) TRY(ensure(h, h->Z, (size_t)NT * J));
+    const size_t wantq = (size_t)NT * NL * std::max(g.mr, h->reserve_m);
+    TRY(ensure(h, h->Q, (size_t)NT * J, wantq));
+    if (mode == FAT_GRAD) TRY(ensure(h, h->Z, (size_t)NT * J, wantq));
     {
       PhaseTimer t(h, PH_PROJ);
       krgemm(h->st, 4, le.p, g.ml, g.ml, featp(h, b), featp(h, b + 1), 1, X, J, (int)J, h->Q.p, J, NT, h->num_sm);
@@ -546,13 +557,13 @@ int grad_from_P(tnml_handle h, double* hstats) {
     PhaseTimer t(h, PH_FAT);
     if (h->cls != 1) {
       const EnvRef& fat = (h->cls == 0) ? re : le;
-      TRY(ensure(h, h->Z, (size_t)NT * fat.m));
+      TRY(ensure(h, h->Z, (size_t)NT * fat.m, (size_t)NT * std::max(fat.m, h->reserve_m)));
       fat_kernel(h->st, FAT_BWD, h->Q.p, fat.p, fat.m, h->labels, h->P, h->Z.p, h->pred, h->stats_partial,
                  h->nfat_blocks, NT);
       h->stats.alg_bytes += 8.0 * NT * ((double)NL * fat.m + fat.m + NL);
       h->stats.alg_flops += (double)NT * 2.0 * NL * fat.m;
     } else {
-      TRY(ensure(h, h->Z, (size_t)NT * NL * g.mr));
+      TRY(ensure(h, h->Z, (size_t)NT * NL * g.mr, (size_t)NT * NL * std::max(g.mr, h->reserve_m)));
       fat_kernel(h->st, FAT_BWD_OUTER, re.p, h->Q.p, g.mr, h->labels, h->P, h->Z.p, h->pred, h->stats_partial,
                  h->nfat_blocks, NT);
     }
@@ -660,9 +671,11 @@ int set_site_dev(tnml_handle h, int j, int ml, int mr, int lab) {
   if (n > s.cap) {
     if (s.d) CK(cudaFreeAsync(s.d, h->st));
     s.d = nullptr;
+    const size_t rm = (size_t)std::min(h->reserve_m, 1024);   // site tensors are small: size them for maxm at once
+    const size_t want = std::max(n, std::max(rm * 2 * rm * (lab ? NL : 1), s.cap + s.cap / 2));
     s.cap = 0;
-    CK(cudaMallocAsync(&s.d, n * sizeof(double), h->st));
-    s.cap = n;
+    CK(cudaMallocAsync(&s.d, want * sizeof(double), h->st));
+    s.cap = want;
   }
   s.ml = ml;
   s.mr = mr;
@@ -744,7 +757,8 @@ int tnml_destroy(tnml_handle h) {
                   h->svd.M, h->svd.tau, h->svd.ready, h->svd.Y, h->svd.M2, h->svd.tau2, h->svd.Y2, h->svd.perm0};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  if (h->svd.gexec) cudaGraphExecDestroy(h->svd.gexec);
+  for (auto& ge : h->svd.gexec)
+    if (ge) cudaGraphExecDestroy(ge);
   if (h->hpin) cudaFreeHost(h->hpin);
   for (auto& e : h->evs) {
     cudaEventDestroy(e.a);
@@ -1028,6 +1042,7 @@ int tnml_svd_split(tnml_handle h, int dir, double cutoff, int maxm, int minm, in
   int m = 0, sweeps = 0;
   double terr = 0.0;
   int rc;
+  h->svd.hint_m = std::max(h->reserve_m, maxm < 4096 ? maxm : 0);
   {
     PhaseTimer t(h, PH_SVD);
     rc = svd_split(h->st, h->svd, h->B.p, g, dir, cutoff, maxm, minm, do_rel_cutoff, h->W[b].d, h->W[b + 1].d, &m,

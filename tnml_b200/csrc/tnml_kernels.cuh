@@ -92,8 +92,15 @@ struct SvdWork {
   int* perm0 = nullptr;    // [ns] columns of X sorted by decreasing norm
   long capM2 = 0;
   int use_qr = -1;         // -1 auto, 0 never, 1 one QR, 3 sort + two QRs (TNML_SVD_QR)
-  cudaGraphExec_t gexec = nullptr;   // one Jacobi sweep, captured for the current (buffers, dims)
-  long gkey[6] = {0, 0, 0, 0, 0, 0};
+  int hint_m = 0;          // largest link dimension expected (maxm): buffers are sized for it at once
+  // one Jacobi sweep captured as a CUDA graph, one executable per (buffers, dims) seen -- in a real
+  // sweep the bond matrix has a different size at almost every bond, and re-instantiating the
+  // graph every time costs more than it saves
+  static constexpr int NGRAPH = 96;
+  cudaGraphExec_t gexec[NGRAPH] = {};
+  long gkey[NGRAPH][6] = {};
+  long gstamp[NGRAPH] = {};
+  long gclock = 0;
 };
 // Gather canonical B into X (tall orientation), run block one-sided Jacobi,
 // sort, apply ITensor's truncation rule, scatter U -> W(c), S*V -> W(c+dc).

@@ -14,6 +14,7 @@
 // (fixedL.cc:593) forces the trailing vectors to be kept.
 #include "tnml_kernels.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1119,6 +1120,15 @@ __global__ void svd_scatter_qr_kernel(const double* __restrict__ Y, const double
 }
 
 static int ensure(SvdWork& w, long nX, int ns) {
+  // cudaMalloc / cudaFree synchronise the device and were measured at up to 1.4 s next to a large
+  // stream-ordered pool: size every buffer for the largest bond matrix (2*maxm*NL x 2*maxm) at once
+  if (w.hint_m > 0) {
+    const long hs = 2L * w.hint_m;
+    if (ns <= hs && nX <= hs * hs * NL) {
+      ns = (int)std::max<long>(ns, hs);
+      nX = std::max(nX, hs * hs * NL);
+    }
+  }
   if (nX > w.capX) {
     if (w.X) cudaFree(w.X);
     if (cudaMalloc(&w.X, nX * sizeof(double)) != cudaSuccess) return -1;
@@ -1227,11 +1237,22 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
     if (gram) {
       // one sweep = nblk_e-1 launches + bookkeeping; replayed as a CUDA graph (the launch gaps of
       // ~300 back-to-back 10 us kernels were ~0.8 ms per SVD)
-      cudaGraphExec_t& gexec = w.gexec;
-      long* gkey = w.gkey;
       const long key[6] = {(long)(size_t)A, (long)(size_t)Jm, rows, ns, GW, (long)(size_t)w.info};
-      bool same = gexec != nullptr;
-      for (int i = 0; i < 6; ++i) same = same && (gkey[i] == key[i]);
+      int gi = -1, lru = 0;
+      for (int k = 0; k < SvdWork::NGRAPH; ++k) {
+        bool eq = w.gexec[k] != nullptr;
+        for (int i = 0; i < 6 && eq; ++i) eq = (w.gkey[k][i] == key[i]);
+        if (eq) {
+          gi = k;
+          break;
+        }
+        if (w.gstamp[k] < w.gstamp[lru]) lru = k;
+      }
+      bool same = gi >= 0;
+      if (!same) gi = lru;
+      w.gstamp[gi] = ++w.gclock;
+      cudaGraphExec_t& gexec = w.gexec[gi];
+      long* gkey = w.gkey[gi];
       static int use_graph = -1;
       if (use_graph < 0) use_graph = getenv("TNML_SVD_NOGRAPH") ? 0 : 1;
       auto enqueue = [&]() {
