@@ -276,6 +276,43 @@ def test_fixedL_binary_matches_capi(capi, tmp_path):
     h.close()
 
 
+@pytest.mark.parametrize("m0,NT", [(6, 700), (7, 1100), (13, 2500)])
+def test_krgemm_variants_agree(capi, m0, NT):
+    """The persistent projection kernel (output-side Khatri-Rao weights, cp.async A tiles, resident
+    B panel; used from 512 rows on) against the register-staged kernel and the oracle: environment
+    advance (S=2), projection / cost (S=4) on every bond class, even and odd link dimensions
+    (16-byte and 8-byte cp.async paths)."""
+    feat, labels, W = make_problem(N=12, NT=NT, m0=m0)
+    ts = O.TrainStates(feat, labels)
+    ts.init(copy_mps(W))
+    res = {}
+    for variant in (1, 2):
+        h = capi.Handle(0)
+        h.set_option("krgemm_variant", variant)
+        h.set_images(feat, labels.astype(np.int32))
+        h.set_mps(W)
+        h.init_envs()
+        out = []
+        for b in range(1, 12):
+            h.set_bond(b)
+            h.bond_form()
+            C, CL, nc = h.quadcost(False, 0.0)
+            out.append((C, nc))
+            h.shift_env(b, capi.FROMLEFT)
+        res[variant] = (out, [h.get_env(j) for j in (3, 5, 6, 9)])
+        h.set_option("krgemm_variant", 2)
+        h.close()
+    for (c1, n1), (c2, n2) in zip(res[1][0], res[2][0]):
+        assert abs(c1 - c2) <= 1e-12 * abs(c1) and n1 == n2
+    for e1, e2 in zip(res[1][1], res[2][1]):
+        assert rel(e2, e1) < 1e-13
+    for b in range(1, 12):          # and against the oracle
+        ts.set_bond(b)
+        Co, _, nco = O.quadcost(O.form_bond(W[b], W[b + 1]), ts, detail=True)
+        assert abs(res[2][0][b - 1][0] - Co) <= 1e-11 * Co and res[2][0][b - 1][1] == nco
+        ts.shiftE(W, b, "Fromleft")
+
+
 def test_env_tier_bit_identical(capi):
     """environment tiering.  With an HBM budget that holds only a handful of
     environment slots (the rest live in pinned host memory, fetched ahead on a copy stream) two

@@ -1206,6 +1206,10 @@ int tnml_set_option(tnml_handle h, const char* name, double value) {
     h->cg_reuse_forward = (value != 0.0);
     return TNML_OK;
   }
+  if (strcmp(name, "krgemm_variant") == 0) {   // process-wide (testing / A-B timing)
+    krgemm_set_variant((int)value);
+    return TNML_OK;
+  }
   if (strcmp(name, "env_budget_gb") == 0) {
     if (value < 0) return fail(h, TNML_ERR_INVALID, "env_budget_gb must be >= 0");
     h->env_budget = (size_t)(value * 1073741824.0);

@@ -9,6 +9,7 @@
 #include "tnml_kernels.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace tnml {
 
@@ -160,9 +161,283 @@ krgemm_kernel(const double* __restrict__ In, long ldin, int ma, const double* __
   }
 }
 
+// ---------------------------------------------------------------------------
+// krgemm2: the same contraction with the Khatri-Rao weights moved to the OUTPUT side,
+//   Out[row][j] = sum_p w_p(row) * ( sum_a In[row][a] * Bm[(a*S+p)*ldb + j] ),
+// i.e. S plain GEMMs with K = ma sharing the A operand, combined in the epilogue.  Motivation
+// (ncu source view of krgemm_kernel<4>, profiles/r01): 19 % of the stall samples sit on the
+// per-k-tile barrier and 14 % on the DMULs that generate In*w_p (they queue behind the DMMAs on
+// the one FP64 pipe).  Here the A operand is the raw environment slice, so
+//   * it is staged by cp.async (no register staging, no multiplies);
+//   * every WARP runs its own 3-stage cp.async pipeline over its own 16-row tiles -- no block or
+//     group barrier in the main loop, the warps drift freely and keep the DMMA pipe fed (the
+//     first version with 128-row tiles shared by 8 warps still lost 9 % to the barrier);
+//   * the pipeline runs across tile boundaries (the next tile's stages are in flight during the
+//     epilogue of the current one);
+//   * the B panel (all K rows x 16 columns) stays resident in shared memory for the whole CTA.
+// One persistent 512-thread CTA per SM; every warp owns a contiguous range of rows cut in 16-row
+// tiles, a last tile of <= 8 rows issues only half of the MMAs, so all SMs get the same work.
+constexpr int G2_BN = 16;     // columns per CTA column tile
+constexpr int G2_BNP = 20;    // padded B row: t-stride of 20 doubles is conflict-free per half warp
+constexpr int G2_AK = 16;     // a-values per A stage
+constexpr int G2_ALD = 20;    // padded A row (row-major tile [16][16+4])
+constexpr int G2_WR = 16;     // rows per warp tile
+constexpr int G2_WARPS = 16;
+
+__device__ __forceinline__ void cp_async8(double* dst, const double* src, int bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16(double* dst, const double* src, int bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// MMAs of k-steps [K0, K1) of one pipeline stage: MI x NI tiles of 8 x 8 per weight index p; only
+// the first k4n k-steps of the stage exist (ma need not be a multiple of 16)
+template <int S, int MI, int NI, int K0, int K1>
+__device__ __forceinline__ void krgemm2_mma(double (&acc)[S][2][2][2], const double* __restrict__ Asb,
+                                            const double* __restrict__ Bsb, int pstride, int k4n) {
+#pragma unroll
+  for (int k4 = K0; k4 < K1; ++k4) {
+    if (k4 < k4n) {
+      double af[MI], bf[S][NI];
+#pragma unroll
+      for (int mi = 0; mi < MI; ++mi) af[mi] = Asb[mi * 8 * G2_ALD + k4 * 4];
+#pragma unroll
+      for (int p = 0; p < S; ++p) {
+        const double* bp = Bsb + p * pstride + k4 * 4 * G2_BNP;
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) bf[p][ni] = bp[ni * 8];
+      }
+#pragma unroll
+      for (int p = 0; p < S; ++p)
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < NI; ++ni) dmma884(acc[p][mi][ni][0], acc[p][mi][ni][1], af[mi], bf[p][ni]);
+    }
+  }
+}
+template <int S, int K0, int K1>
+__device__ __forceinline__ void krgemm2_mma_sel(double (&acc)[S][2][2][2], const double* __restrict__ Asb,
+                                                const double* __restrict__ Bsb, int pstride, int k4n, int bmt,
+                                                int nin) {
+  // only the MMAs that produce existing rows / columns are issued: a last row tile of <= 8 rows
+  // drops rows 8..15, a last column tile of <= 8 columns drops columns 8..15
+  if (bmt > 8) {
+    if (nin == 2) krgemm2_mma<S, 2, 2, K0, K1>(acc, Asb, Bsb, pstride, k4n);
+    else krgemm2_mma<S, 2, 1, K0, K1>(acc, Asb, Bsb, pstride, k4n);
+  } else {
+    if (nin == 2) krgemm2_mma<S, 1, 2, K0, K1>(acc, Asb, Bsb, pstride, k4n);
+    else krgemm2_mma<S, 1, 1, K0, K1>(acc, Asb, Bsb, pstride, k4n);
+  }
+}
+
+template <int S, int STAGES>
+__global__ void __launch_bounds__(32 * G2_WARPS, 1)
+krgemm2_kernel(const double* __restrict__ In, long ldin, int ma, const double* __restrict__ f1,
+               const double* __restrict__ f2, int div, const double* __restrict__ Bm, long ldb, int J,
+               double* __restrict__ Out, long ldout, long rows, int X, int P, int ma_pad, int vec16) {
+  extern __shared__ __align__(16) double smem[];
+  double* Bs = smem;                                            // [S][ma_pad][G2_BNP]
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+  double* Aw = smem + (long)S * ma_pad * G2_BNP + (long)wid * STAGES * G2_WR * G2_ALD;   // [STAGES][16][G2_ALD]
+  const int cg = blockIdx.x % X, y = blockIdx.x / X;
+  const int coltiles = (J + G2_BN - 1) / G2_BN;
+  const int nk = ma_pad / G2_AK;
+  // contiguous row range of this warp (worker w of W)
+  const long W = (long)G2_WARPS * P, w = (long)G2_WARPS * y + wid;
+  const long rbeg = (rows * w) / W, rend = (rows * (w + 1)) / W;
+  const long ntile = (rend - rbeg + G2_WR - 1) / G2_WR;
+
+  // Prefetch cursor: the A chunk (16 rows x 16 a) of step (pf_tile, pf_kt) goes to stage pf_stage.
+  // All per-lane offsets are loop invariants; the cursor advances without divisions.  The ncu
+  // source view of the first version showed 2 IMADs per DMMA and all four warps of a scheduler
+  // doing this bookkeeping at the same time (DMMA pipe idle 25 %), so (a) it is cheap now and
+  // (b) it is issued in the MIDDLE of the MMA block of the current step, where the DMMA queue
+  // hides it.
+  // lane -> (row r0 + c*rstep, a-offset q0) of its c-th copy: 4 copies of 16 B or 8 copies of 8 B
+  const int r0 = vec16 ? (lane >> 3) : (lane >> 4);
+  const int q0 = vec16 ? 2 * (lane & 7) : (lane & 15);
+  const int rstep = vec16 ? 4 : 2;
+  const int dst_lane = r0 * G2_ALD + q0;
+  const long src_lane = (long)r0 * ldin + q0;
+  const long src_step = (long)rstep * ldin;
+  const int pstride = ma_pad * G2_BNP;
+  long pf_tile = 0;
+  int pf_kt = 0, pf_stage = 0;
+  auto issue_next = [&]() {
+    if (pf_tile < ntile) {
+      const long row0 = rbeg + pf_tile * G2_WR;
+      const int bmt = (int)((rend - row0 < G2_WR) ? (rend - row0) : G2_WR);
+      const int a = pf_kt * G2_AK + q0;
+      double* dst = Aw + pf_stage * (G2_WR * G2_ALD) + dst_lane;
+      const double* src = In + row0 * ldin + pf_kt * G2_AK + src_lane;
+      if (vec16) {
+        const int abytes = (a < ma) ? ((ma - a >= 2) ? 16 : 8) : 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const bool ok = (r0 + 4 * c < bmt) && (abytes > 0);
+          cp_async16(dst + c * 4 * G2_ALD, ok ? (src + c * src_step) : In, ok ? abytes : 0);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const bool ok = (r0 + 2 * c < bmt) && (a < ma);
+          cp_async8(dst + c * 2 * G2_ALD, ok ? (src + c * src_step) : In, ok ? 8 : 0);
+        }
+      }
+      if (++pf_kt == nk) {
+        pf_kt = 0;
+        ++pf_tile;
+      }
+      if (++pf_stage == STAGES) pf_stage = 0;
+    }
+    cp_async_commit();
+  };
+  (void)rstep;
+
+  for (int ct = cg; ct < coltiles; ct += X) {
+    const int j0 = ct * G2_BN;
+    const int nin = (J - j0 > 8) ? 2 : 1;
+    __syncthreads();   // every warp is done with the previous B panel
+    for (int idx = tid; idx < S * ma_pad * G2_BN; idx += 32 * G2_WARPS) {
+      const int n = idx & (G2_BN - 1);
+      const int k2 = idx >> 4;            // = a*S + p
+      const int a = k2 / S, p = k2 - a * S;
+      const double v = (a < ma && j0 + n < J) ? Bm[(long)k2 * ldb + j0 + n] : 0.0;
+      Bs[(p * ma_pad + a) * G2_BNP + n] = v;
+    }
+    __syncthreads();
+    double acc[S][2][2][2];
+#pragma unroll
+    for (int p = 0; p < S; ++p)
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) acc[p][mi][ni][0] = acc[p][mi][ni][1] = 0.0;
+    pf_tile = 0;
+    pf_kt = 0;
+    pf_stage = 0;
+#pragma unroll
+    for (int s0 = 0; s0 < STAGES - 1; ++s0) issue_next();
+    int stage = 0;
+    for (long tile = 0; tile < ntile; ++tile) {
+      const long row0 = rbeg + tile * G2_WR;
+      const int bmt = (int)((rend - row0 < G2_WR) ? (rend - row0) : G2_WR);
+      for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncwarp();   // this stage visible to all lanes; all lanes finished reading the previous one
+        const double* Asb = Aw + stage * (G2_WR * G2_ALD) + g * G2_ALD + tq;
+        const double* Bsb = Bs + (kt * G2_AK + tq) * G2_BNP + g;
+        const int rem = ma - kt * G2_AK;
+        const int k4n = (rem >= G2_AK) ? (G2_AK / 4) : ((rem + 3) >> 2);
+        krgemm2_mma_sel<S, 0, 1>(acc, Asb, Bsb, pstride, k4n, bmt, nin);
+        issue_next();   // refills the stage read in the previous step
+        krgemm2_mma_sel<S, 1, G2_AK / 4>(acc, Asb, Bsb, pstride, k4n, bmt, nin);
+        if (++stage == STAGES) stage = 0;
+      }
+      // tile finished: combine the S partial products with the row's weights
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int lr = mi * 8 + g;
+        if (lr < bmt) {
+          const long r = row0 + lr;
+          double wgt[S];
+          kr_weights<S>(f1, f2, r / div, wgt);
+#pragma unroll
+          for (int ni = 0; ni < 2; ++ni) {
+            double o0 = 0.0, o1 = 0.0;
+#pragma unroll
+            for (int p = 0; p < S; ++p) {
+              o0 = fma(wgt[p], acc[p][mi][ni][0], o0);
+              o1 = fma(wgt[p], acc[p][mi][ni][1], o1);
+            }
+            const int j = j0 + ni * 8 + 2 * tq;
+            if (j < J) Out[r * ldout + j] = o0;
+            if (j + 1 < J) Out[r * ldout + j + 1] = o1;
+          }
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < S; ++p)
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 2; ++ni) acc[p][mi][ni][0] = acc[p][mi][ni][1] = 0.0;
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+  }
+}
+
+// returns false when the resident B panel does not fit (large ma): caller falls back to krgemm_kernel
+template <int S>
+static bool krgemm2_launch(cudaStream_t st, const double* In, long ldin, int ma, const double* f1, const double* f2,
+                           int div, const double* Bm, long ldb, int J, double* Out, long ldout, long rows,
+                           int num_sm) {
+  const int ma_pad = ((ma + G2_AK - 1) / G2_AK) * G2_AK;
+  const size_t bbytes = (size_t)S * ma_pad * G2_BNP * sizeof(double);
+  const size_t a3 = (size_t)G2_WARPS * 3 * G2_WR * G2_ALD * sizeof(double);
+  const size_t a2 = (size_t)G2_WARPS * 2 * G2_WR * G2_ALD * sizeof(double);
+  const size_t lim = 227 * 1024;
+  int stages = 0;
+  if (bbytes + a3 <= lim) stages = 3;
+  else if (bbytes + a2 <= lim) stages = 2;
+  if (!stages) return false;
+  const int coltiles = (J + G2_BN - 1) / G2_BN;
+  // X column groups x P CTAs each: maximise (SMs used) x (column-tile balance)
+  int X = 1, P = num_sm;
+  double best = -1.0;
+  for (int x = 1; x <= coltiles && x <= num_sm; ++x) {
+    const int pp = num_sm / x;
+    const double util = (double)(x * pp) / num_sm;
+    const double bal = (double)coltiles / ((double)x * ((coltiles + x - 1) / x));
+    // rows are split over 16*pp warps: very short ranges waste the pipeline fill
+    const double rowsper = (double)rows / ((double)G2_WARPS * pp);
+    const double fill = rowsper / (rowsper + 4.0);
+    const double score = util * bal * fill;
+    if (score > best + 1e-12) {
+      best = score;
+      X = x;
+      P = pp;
+    }
+  }
+  const int vec16 = ((ldin & 1) == 0 && (((size_t)In) & 15) == 0) ? 1 : 0;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(krgemm2_kernel<S, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim);
+    cudaFuncSetAttribute(krgemm2_kernel<S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim);
+    attr = true;
+  }
+  if (stages == 3)
+    krgemm2_kernel<S, 3><<<X * P, 32 * G2_WARPS, bbytes + a3, st>>>(In, ldin, ma, f1, f2, div, Bm, ldb, J, Out, ldout,
+                                                                  rows, X, P, ma_pad, vec16);
+  else
+    krgemm2_kernel<S, 2><<<X * P, 32 * G2_WARPS, bbytes + a2, st>>>(In, ldin, ma, f1, f2, div, Bm, ldb, J, Out, ldout,
+                                                                  rows, X, P, ma_pad, vec16);
+  return true;
+}
+
+static int g_krgemm_variant = -1;
+void krgemm_set_variant(int v) { g_krgemm_variant = v; }
+
 void krgemm(cudaStream_t st, int S, const double* In, long ldin, int ma, const double* f1, const double* f2,
             int div, const double* Bm, long ldb, int J, double* Out, long ldout, long rows, int num_sm) {
   if (rows <= 0 || J <= 0) return;
+  if (g_krgemm_variant < 0) {   // TNML_KRGEMM=1: register-staged kernel only (A/B comparisons)
+    const char* e = getenv("TNML_KRGEMM");
+    g_krgemm_variant = e ? atoi(e) : 2;
+  }
+  if (g_krgemm_variant == 2 && rows >= 512) {
+    const bool ok = (S == 2) ? krgemm2_launch<2>(st, In, ldin, ma, f1, f2, div, Bm, ldb, J, Out, ldout, rows, num_sm)
+                             : krgemm2_launch<4>(st, In, ldin, ma, f1, f2, div, Bm, ldb, J, Out, ldout, rows, num_sm);
+    if (ok) return;
+  }
   const int coltiles = (J + BN - 1) / BN;
   // rows per tile (multiple of the 16-row warp tile): minimise the makespan
   // ceil(tiles / SMs) * (bm + fixed per-tile overhead) -- the FP64 pipe is the bottleneck, so an

@@ -18,6 +18,9 @@ constexpr int NL = 10;
 // environment advance (fixedL.cc:144-150, 221-229).
 void krgemm(cudaStream_t st, int S, const double* In, long ldin, int ma, const double* f1, const double* f2,
             int div, const double* Bm, long ldb, int J, double* Out, long ldout, long rows, int num_sm);
+// 2 (default): persistent kernel with output-side Khatri-Rao weights, cp.async-staged A tiles and a
+// resident B panel (from 512 rows on, while the panel fits); 1: register-staged kernel only
+void krgemm_set_variant(int v);
 
 // krgram: Gpart[split][(a*S+p)][j] = sum_{row in split} In[row][a] * w_p(row) * Z[row][j]
 // The rank-1 gradient accumulation of fixedL.cc:379,418 as one K=NT contraction, split-K over
