@@ -203,7 +203,7 @@ __device__ __forceinline__ void krgemm2_mma(double (&acc)[S][2][2][2], const dou
                                             const double* __restrict__ Bsb, int pstride, int k4n) {
 #pragma unroll
   for (int k4 = K0; k4 < K1; ++k4) {
-    if (k4 < k4n) {
+    if (k4n >= G2_AK / 4 || k4 < k4n) {
       double af[MI], bf[S][NI];
 #pragma unroll
       for (int mi = 0; mi < MI; ++mi) af[mi] = Asb[mi * 8 * G2_ALD + k4 * 4];
@@ -277,14 +277,22 @@ krgemm2_kernel(const double* __restrict__ In, long ldin, int ma, const double* _
       const int a = pf_kt * G2_AK + q0;
       double* dst = Aw + pf_stage * (G2_WR * G2_ALD) + dst_lane;
       const double* src = In + row0 * ldin + pf_kt * G2_AK + src_lane;
+#ifdef KR2_NO_CPASYNC
+      if (false) {
+#else
       if (vec16) {
+#endif
         const int abytes = (a < ma) ? ((ma - a >= 2) ? 16 : 8) : 0;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const bool ok = (r0 + 4 * c < bmt) && (abytes > 0);
           cp_async16(dst + c * 4 * G2_ALD, ok ? (src + c * src_step) : In, ok ? abytes : 0);
         }
+#ifdef KR2_NO_CPASYNC
+      } else if (false) {
+#else
       } else {
+#endif
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const bool ok = (r0 + 2 * c < bmt) && (a < ma);
@@ -336,12 +344,23 @@ krgemm2_kernel(const double* __restrict__ In, long ldin, int ma, const double* _
         const double* Bsb = Bs + (kt * G2_AK + tq) * G2_BNP + g;
         const int rem = ma - kt * G2_AK;
         const int k4n = (rem >= G2_AK) ? (G2_AK / 4) : ((rem + 3) >> 2);
-        krgemm2_mma_sel<S, 0, 1>(acc, Asb, Bsb, pstride, k4n, bmt, nin);
-        issue_next();   // refills the stage read in the previous step
-        krgemm2_mma_sel<S, 1, G2_AK / 4>(acc, Asb, Bsb, pstride, k4n, bmt, nin);
+        if (k4n == G2_AK / 4 && bmt > 8 && nin == 2) {
+          // common case, no conditions inside: the compiler software-pipelines the fragment loads
+          // of k-step k+1 under the MMAs of k-step k
+          krgemm2_mma<S, 2, 2, 0, 1>(acc, Asb, Bsb, pstride, 4);
+          issue_next();   // refills the stage read in the previous step
+          krgemm2_mma<S, 2, 2, 1, G2_AK / 4>(acc, Asb, Bsb, pstride, 4);
+        } else {
+          krgemm2_mma_sel<S, 0, 1>(acc, Asb, Bsb, pstride, k4n, bmt, nin);
+          issue_next();
+          krgemm2_mma_sel<S, 1, G2_AK / 4>(acc, Asb, Bsb, pstride, k4n, bmt, nin);
+        }
         if (++stage == STAGES) stage = 0;
       }
       // tile finished: combine the S partial products with the row's weights
+#ifdef KR2_NO_EPILOGUE
+      if (acc[0][0][0][0] == 1.2345e300)
+#endif
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi) {
         const int lr = mi * 8 + g;
