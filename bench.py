@@ -351,7 +351,7 @@ def run_ours(args):
         n_gemm = ((npass + 2) if reuse else (2 * npass + 1)) * K   # krgemm launches in K bond updates
         n_fwd = (2 * npass + 1) * K          # fat-kernel launches (passes over the fat environment)
         n_bwd = npass * K                    # krgram launches
-        # --- dominant data-parallel kernel: krgemm<4> (FP64 tensor-core MMAs, DMMA.8x8x4)
+        # --- dominant data-parallel kernel: krgemm2_kernel<4,3> (FP64 tensor-core MMAs, DMMA.8x8x4)
         # algorithmic flops per launch = 2 * NT * (4*m_l) * m_r  (8 m_l m_r per image)
         gemm_flops_launch = 8.0 * NT * m * m
         gemm_ms_launch = stt.ms_proj / max(1, n_gemm)
@@ -359,13 +359,14 @@ def run_ours(args):
         FP64_TENSOR_PEAK = 37.0   # TF/s, measured on this pool with tools/dmma_bench.cu (DMMA and DFMA share it)
         traffic = None
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))["kernels"]["krgemm"]
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))["kernels"]["krgemm2"]
             rd = float(prof["dram__bytes_read.sum"].split()[0]) * (1e6 if "Mbyte" in prof["dram__bytes_read.sum"] else 1e3)
             wr = float(prof["dram__bytes_write.sum"].split()[0]) * (1e6 if "Mbyte" in prof["dram__bytes_write.sum"] else 1e3)
             traffic = (rd + wr) * (NT / 30000.0)       # captured at NT=30000 (ncu cannot replay 62 GB), linear in NT
         except Exception:
             pass
-        roof = {"bound": "tensor", "kernel": "krgemm_kernel<4> (Khatri-Rao projection GEMM, FP64 mma.sync m8n8k4)",
+        roof = {"bound": "tensor", "kernel": "krgemm2_kernel<4,3> (Khatri-Rao projection GEMM, FP64 mma.sync m8n8k4, "
+                                            "cp.async-staged, persistent)",
                 "achieved": gemm_tf, "peak": FP64_TENSOR_PEAK, "unit": "TFLOP/s", "frac": gemm_tf / FP64_TENSOR_PEAK,
                 "traffic": traffic,
                 "peak_source": "FP64 tensor/FMA pipe measured with tools/dmma_bench.cu on this pool's B200 (37.0 TF/s); "
@@ -381,8 +382,8 @@ def run_ours(args):
                     "algorithmic_bytes_per_launch": 8.0 * NT * (11 * m + 1)}
         # --- the serial term: truncated SVD of the 2m x 2m bond matrix (replicated on every rank)
         svd_info = {"ms_per_step": stt.ms_svd / K, "sweeps": [int(r.svd_sweeps) for r in res_t][:8],
-                    "note": "Householder QR + Gram-based block Jacobi (latency bound, ~15 CTAs); largest summed "
-                            "share of the step, see profiles/r01_ncu_summary.md"}
+                    "note": "column sort + 2 Householder QRs + Gram-based block Jacobi (latency bound, ~15 CTAs); "
+                            "largest summed share of the step, see profiles/r01_ncu_summary.md"}
         line = {"metric": "bond-updates/sec", "value": value, "unit": "bond-updates/sec", "n_gpus": world,
                 "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, world),

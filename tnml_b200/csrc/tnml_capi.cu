@@ -754,7 +754,7 @@ int tnml_destroy(tnml_handle h) {
     if (b->p) cudaFree(b->p);
   void* ptrs[] = {h->feat, h->labels, h->ones, h->P, h->PV, h->pred, h->stats_partial, h->dscal, h->dot_scratch,
                   h->svd.X, h->svd.J, h->svd.sig2, h->svd.perm, h->svd.info, h->svd.flags,
-                  h->svd.M, h->svd.tau, h->svd.ready, h->svd.Y, h->svd.M2, h->svd.tau2, h->svd.Y2, h->svd.perm0};
+                  h->svd.M, h->svd.tau, h->svd.ready, h->svd.Y, h->svd.M2, h->svd.tau2, h->svd.Y2, h->svd.perm0, h->svd.sweepmax};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& ge : h->svd.gexec)

@@ -80,6 +80,7 @@ struct SvdWork {
   int* perm = nullptr;     // [small]
   double* info = nullptr;  // [8]: 0 maxoff of last sweep, 1 newm, 2 truncerr, 3 sweeps, 4 sum sig2
   int* flags = nullptr;    // [4]: 0 converged
+  double* sweepmax = nullptr;  // [64] largest rotated cos^2 per sweep (cluster-resident Jacobi)
   long capX = 0, capJ = 0;
   int capS = 0;
   // QR-preconditioned path

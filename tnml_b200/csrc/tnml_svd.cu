@@ -14,6 +14,8 @@
 // (fixedL.cc:593) forces the trailing vectors to be kept.
 #include "tnml_kernels.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -587,6 +589,278 @@ jacobi_gram_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows, in
   if (g_qr_dbg != nullptr && tid == 0 && blockIdx.x == 0) {
     tstamp[5] = clock64();
     for (int i = 0; i < 6; ++i) g_qr_dbg[2048 + i] = tstamp[i];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Cluster-resident Jacobi: the whole iteration (all sweeps) in ONE launch of one 16-CTA thread-block
+// cluster.  The working set ([A | J], <= 256 columns x 512 rows = 1 MB) lives in the distributed
+// shared memory of the cluster for the whole SVD: every CTA holds the two 8-column blocks of its
+// current block pair, runs the same Gram / rotation-round / apply phases as jacobi_gram_kernel,
+// and the apply phase stores every updated column DIRECTLY into the shared memory of the CTA
+// that needs it in the next round (st.shared::cluster through a generic pointer).  One
+// cluster barrier per round replaces a kernel boundary; the per-round staging from / write-back
+// to L2 (2.7 of the 11 us per round of the multi-launch version) and the launch gaps disappear.
+// The round-robin tournament is the same circle method, so the rotations are the same.
+__device__ __forceinline__ void rr_where(int n, int r, int x, int& k, int& slot) {
+  // inverse of rr_pair: in round r block x sits in pair k as p (slot 0) or q (slot 1)
+  if (x == n - 1) {
+    k = 0;
+    slot = 0;
+    return;
+  }
+  if (x == r) {
+    k = 0;
+    slot = 1;
+    return;
+  }
+  const int d = (x - r + (n - 1)) % (n - 1);      // x = (r + d) mod (n-1)
+  if (d <= n / 2 - 1) {
+    k = d;
+    slot = 0;
+  } else {
+    k = (n - 1) - d;                               // x = (r - k) mod (n-1)
+    slot = 1;
+  }
+}
+
+template <int W>
+__global__ void __launch_bounds__(32 * W, 1)
+jacobi_cluster_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows, int ns, int ld, int nblk_e,
+                      double tol2, double conv, int max_sweeps, double* __restrict__ info,
+                      double* __restrict__ sweepmax, int* __restrict__ flags) {
+  namespace cg = cooperative_groups;
+  constexpr int NC = 2 * W, NR = NC - 1, NTH = 32 * W, NWARP = NTH / 32, TG = NC / 8;
+  static_assert(W == 8, "cluster kernel is written for 8-column blocks (256 threads)");
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  const int ncta = nblk_e / 2;
+  const bool active = crank < ncta;
+  extern __shared__ __align__(16) double sm[];
+  double* buf0 = sm;                                 // [NC][ld]
+  double* buf1 = sm + (long)NC * ld;                 // [NC][ld]
+  double* G0 = buf1 + (long)NC * ld;                 // [NC][GLD]
+  double* G1 = G0 + NC * GLD;
+  double* RA = G1 + NC * GLD;
+  double* CS = RA + NC * GLD;                        // [2][W][2]
+  double** DST = reinterpret_cast<double**>(CS + 4 * W);   // [NC] destination column of the next round
+  unsigned short* PQ = reinterpret_cast<unsigned short*>(DST + NC);   // [NR][W]
+  unsigned char* POS = reinterpret_cast<unsigned char*>(PQ + NR * W);  // [NR][NC]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int tot = rows + ns;
+  const int rows2 = rows >> 1, tot2 = tot >> 1, ld2 = ld >> 1;
+  const int nrd = nblk_e - 1;                        // rounds per sweep
+
+  // ---- tables + initial load of the block pair of round 0 into buf0
+  for (int i = tid; i < NR * W; i += NTH) {
+    const int rd = i / W, k = i - rd * W;
+    int p, q;
+    rr_pair(NC, rd, k, p, q);
+    PQ[i] = (unsigned short)(p | (q << 8));
+    POS[rd * NC + p] = (unsigned char)(2 * k);
+    POS[rd * NC + q] = (unsigned char)(2 * k + 1);
+  }
+  if (active) {
+    int P, Q;
+    rr_pair(nblk_e, 0, crank, P, Q);
+    for (int i = tid; i < NC * ld2; i += NTH) {
+      const int k = i / ld2, r2 = i - k * ld2;
+      const int c = (k < W) ? (P * W + k) : (Q * W + k - W);
+      double2 v = make_double2(0.0, 0.0);
+      if (c < ns && r2 < tot2)
+        v = (r2 < rows2) ? __ldcg(reinterpret_cast<const double2*>(A + (long)c * rows) + r2)
+                         : __ldcg(reinterpret_cast<const double2*>(Jm + (long)c * ns) + (r2 - rows2));
+      reinterpret_cast<double2*>(buf0 + (long)k * ld)[r2] = v;
+    }
+  }
+  cluster.sync();
+
+  int cur = 0, R = 0, sweeps_done = 0, converged = 0;
+  for (int sw = 0; sw < max_sweeps; ++sw) {
+    double mo = 0.0;
+    for (int rr = 0; rr < nrd; ++rr) {
+      const int Rn = (R + 1 == nrd) ? 0 : R + 1;
+      if (active) {
+        double* S = cur ? buf1 : buf0;
+        double* Sn = cur ? buf0 : buf1;
+        int P, Q;
+        rr_pair(nblk_e, R, crank, P, Q);
+        // destination of every local column in the next round
+        if (tid < NC) {
+          const int blk = (tid < W) ? P : Q;
+          int k2, slot;
+          rr_where(nblk_e, Rn, blk, k2, slot);
+          double* remote = cluster.map_shared_rank(Sn, (unsigned)k2);
+          DST[tid] = remote + (long)(slot * W + (tid & (W - 1))) * ld;
+        }
+        for (int i = tid; i < NC * GLD; i += NTH) RA[i] = ((i / GLD) == (i % GLD)) ? 1.0 : 0.0;
+        // ---- Gram (rows split over two warps per tile, 4 accumulator chains)
+        {
+          const int tile = warp % (TG * TG), kh = warp / (TG * TG);
+          const int ti = tile / TG, tj = tile - ti * TG;
+          const int nk4 = (rows + 3) >> 2;
+          const int kbeg = (nk4 * kh) / 2, kend = (nk4 * (kh + 1)) / 2;
+          const double* pa = S + (long)(ti * 8 + g) * ld + t;
+          const double* pb = S + (long)(tj * 8 + g) * ld + t;
+          double d[4][2];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) d[u][0] = d[u][1] = 0.0;
+          int k = kbeg;
+          for (; k + 4 <= kend; k += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int r0 = (k + u) * 4;
+              const bool ok = (r0 + t) < rows;
+              dmma884s(d[u][0], d[u][1], ok ? pa[r0] : 0.0, ok ? pb[r0] : 0.0);
+            }
+          }
+          for (; k < kend; ++k) {
+            const int r0 = k * 4;
+            const bool ok = (r0 + t) < rows;
+            dmma884s(d[0][0], d[0][1], ok ? pa[r0] : 0.0, ok ? pb[r0] : 0.0);
+          }
+          double* Gd = kh ? G1 : G0;
+          Gd[(ti * 8 + g) * GLD + tj * 8 + 2 * t] = (d[0][0] + d[1][0]) + (d[2][0] + d[3][0]);
+          Gd[(ti * 8 + g) * GLD + tj * 8 + 2 * t + 1] = (d[0][1] + d[1][1]) + (d[2][1] + d[3][1]);
+        }
+        __syncthreads();
+        {
+          const int r = tid / NC, c = tid - r * NC;   // NTH == NC * NC
+          G0[r * GLD + c] += G1[r * GLD + c];
+        }
+        __syncthreads();
+        // ---- rotation rounds on the Gram matrix (identical to jacobi_gram_kernel)
+        double* curG = G0;
+        double* nxtG = G1;
+        if (tid < W) {
+          const int pq = PQ[tid];
+          const int p = pq & 0xff, q = pq >> 8;
+          double c, sn, rot;
+          plane_rot(curG[p * GLD + p], curG[q * GLD + q], curG[p * GLD + q], tol2, c, sn, rot);
+          CS[2 * tid] = c;
+          CS[2 * tid + 1] = sn;
+          mo = fmax(mo, rot);
+        }
+        __syncthreads();
+        constexpr int RE = 2;
+        constexpr int T_BLK = W * W, T_RA = NC * W / RE;
+        static_assert(T_BLK + T_RA + W <= NTH, "thread budget");
+        for (int rd = 0; rd < NR; ++rd) {
+          const double* cs = CS + (rd & 1) * 2 * W;
+          double* csn = CS + ((rd + 1) & 1) * 2 * W;
+          const unsigned short* pqr = PQ + rd * W;
+          if (tid < T_BLK) {
+            const int k = tid / W, l = tid - k * W;
+            const int pqk = pqr[k], pql = pqr[l];
+            const int pk = pqk & 0xff, qk = pqk >> 8, pl = pql & 0xff, ql = pql >> 8;
+            const double ck = cs[2 * k], sk = cs[2 * k + 1], cl = cs[2 * l], sl = cs[2 * l + 1];
+            const double g00 = curG[pk * GLD + pl], g01 = curG[pk * GLD + ql];
+            const double g10 = curG[qk * GLD + pl], g11 = curG[qk * GLD + ql];
+            const double t00 = ck * g00 - sk * g10, t01 = ck * g01 - sk * g11;
+            const double t10 = sk * g00 + ck * g10, t11 = sk * g01 + ck * g11;
+            nxtG[pk * GLD + pl] = t00 * cl - t01 * sl;
+            nxtG[pk * GLD + ql] = t00 * sl + t01 * cl;
+            nxtG[qk * GLD + pl] = t10 * cl - t11 * sl;
+            nxtG[qk * GLD + ql] = t10 * sl + t11 * cl;
+          } else if (tid < T_BLK + T_RA) {
+            const int u = tid - T_BLK, i = u / (W / RE), l0 = (u - i * (W / RE)) * RE;
+#pragma unroll
+            for (int e = 0; e < RE; ++e) {
+              const int pql = pqr[l0 + e];
+              const int pl = pql & 0xff, ql = pql >> 8;
+              const double cl = cs[2 * (l0 + e)], sl = cs[2 * (l0 + e) + 1];
+              const double a = RA[i * GLD + pl], b = RA[i * GLD + ql];
+              RA[i * GLD + pl] = cl * a - sl * b;
+              RA[i * GLD + ql] = sl * a + cl * b;
+            }
+          } else if (tid >= NTH - W && rd + 1 < NR) {
+            const int j = tid - (NTH - W);
+            const int pqn = PQ[(rd + 1) * W + j];
+            const int x = pqn & 0xff, y = pqn >> 8;
+            const int ix = POS[rd * NC + x], iy = POS[rd * NC + y];
+            const int kx = ix >> 1, ky = iy >> 1;
+            const int pqx = pqr[kx], pqy = pqr[ky];
+            const int xp = pqx & 0xff, xq = pqx >> 8, yp = pqy & 0xff, yq = pqy >> 8;
+            const double cx = cs[2 * kx], sx = cs[2 * kx + 1], cy = cs[2 * ky], sy = cs[2 * ky + 1];
+            const double ux = (ix & 1) ? sx : cx, vx = (ix & 1) ? cx : -sx;
+            const double uy = (iy & 1) ? sy : cy, vy = (iy & 1) ? cy : -sy;
+            auto quad = [&](int ap, int aq, double ua, double va, int bp, int bq, double ub, double vb) {
+              const double g00 = curG[ap * GLD + bp], g01 = curG[ap * GLD + bq];
+              const double g10 = curG[aq * GLD + bp], g11 = curG[aq * GLD + bq];
+              return ua * (g00 * ub + g01 * vb) + va * (g10 * ub + g11 * vb);
+            };
+            const double gxx = quad(xp, xq, ux, vx, xp, xq, ux, vx);
+            const double gyy = quad(yp, yq, uy, vy, yp, yq, uy, vy);
+            const double gxy = quad(xp, xq, ux, vx, yp, yq, uy, vy);
+            double c, sn, rot;
+            plane_rot(gxx, gyy, gxy, tol2, c, sn, rot);
+            csn[2 * j] = c;
+            csn[2 * j + 1] = sn;
+            mo = fmax(mo, rot);
+          }
+          __syncthreads();
+          double* tmp = curG;
+          curG = nxtG;
+          nxtG = tmp;
+        }
+        // ---- apply the accumulated rotation; the result goes straight to the next round's owners
+        const int nrb = (tot + 7) / 8;
+        for (int rb = warp; rb < nrb; rb += NWARP) {
+          const int r0 = rb * 8;
+          double acc[TG][2];
+#pragma unroll
+          for (int n = 0; n < TG; ++n) acc[n][0] = acc[n][1] = 0.0;
+#pragma unroll
+          for (int k0 = 0; k0 < NC; k0 += 4) {
+            const double a = S[(long)(k0 + t) * ld + r0 + g];
+#pragma unroll
+            for (int n = 0; n < TG; ++n) {
+              const double b = RA[(k0 + t) * GLD + n * 8 + g];
+              dmma884s(acc[n][0], acc[n][1], a, b);
+            }
+          }
+#pragma unroll
+          for (int n = 0; n < TG; ++n) {
+            DST[n * 8 + 2 * t][r0 + g] = acc[n][0];
+            DST[n * 8 + 2 * t + 1][r0 + g] = acc[n][1];
+          }
+        }
+      }
+      cluster.sync();   // every column of the next round has arrived; this round's buffer is free
+      cur ^= 1;
+      R = Rn;
+    }
+    // ---- end of sweep: largest rotated cos^2 over the cluster
+    if (active && (tid < W || tid >= NTH - W) && mo > 0.0) atomic_max_pos(sweepmax + sw, mo);
+    __threadfence();
+    cluster.sync();
+    const double smax = __ldcg(sweepmax + sw);
+    sweeps_done = sw + 1;
+    if (smax <= conv) {
+      converged = 1;
+      break;
+    }
+  }
+  // ---- write the blocks this CTA holds (pair of round R) back to global memory
+  if (active) {
+    const double* S = cur ? buf1 : buf0;
+    int P, Q;
+    rr_pair(nblk_e, R, crank, P, Q);
+    for (int i = tid; i < NC * ld2; i += NTH) {
+      const int k = i / ld2, r2 = i - k * ld2;
+      const int c = (k < W) ? (P * W + k) : (Q * W + k - W);
+      if (c < ns && r2 < tot2) {
+        const double2 v = reinterpret_cast<const double2*>(S + (long)k * ld)[r2];
+        if (r2 < rows2)
+          __stcg(reinterpret_cast<double2*>(A + (long)c * rows) + r2, v);
+        else
+          __stcg(reinterpret_cast<double2*>(Jm + (long)c * ns) + (r2 - rows2), v);
+      }
+    }
+  }
+  if (crank == 0 && tid == 0) {
+    info[3] += (double)sweeps_done;
+    flags[0] = converged;
   }
 }
 
@@ -1175,6 +1449,7 @@ static int ensure(SvdWork& w, long nX, int ns) {
   if (!w.info) {
     if (cudaMalloc(&w.info, 8 * sizeof(double)) != cudaSuccess) return -1;
     if (cudaMalloc(&w.flags, 4 * sizeof(int)) != cudaSuccess) return -1;
+    if (cudaMalloc(&w.sweepmax, 64 * sizeof(double)) != cudaSuccess) return -1;
   }
   if (nJ > w.capM) {   // QR path: R^T, tau, ready flags
     if (w.M) cudaFree(w.M);
@@ -1258,6 +1533,56 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
   const double conv = gram ? gram_conv : (Wd ? tol2 : tol);
   const int max_sweeps = 60;
   int hflag = 0;
+  // ---- cluster-resident path: all sweeps in one launch of a 16-CTA cluster (<= 256 columns)
+  static int use_cluster = -1;
+  if (use_cluster < 0) {
+    const char* e = getenv("TNML_SVD_CLUSTER");
+    use_cluster = e ? atoi(e) : 1;
+    if (use_cluster) {
+      if (cudaFuncSetAttribute(jacobi_cluster_kernel<8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+          cudaFuncSetAttribute(jacobi_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
+        cudaGetLastError();
+        use_cluster = 0;
+      }
+    }
+  }
+  if (gram && use_cluster && GW == 8 && nblk_e <= 32) {
+    const size_t need_cl = ((size_t)2 * 16 * gld + 3 * 16 * GLD + 4 * 8) * sizeof(double) + 16 * sizeof(double*) +
+                           (size_t)15 * 8 * sizeof(unsigned short) + (size_t)15 * 16 + 16;
+    if (need_cl <= 220 * 1024) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(16, 1, 1);
+      cfg.blockDim = dim3(256, 1, 1);
+      cfg.dynamicSmemBytes = need_cl;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 16;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      static int checked = 0;
+      if (!checked) {
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, jacobi_cluster_kernel<8>, &cfg) != cudaSuccess || ncl < 1) {
+          cudaGetLastError();
+          use_cluster = 0;
+        }
+        checked = 1;
+      }
+      if (use_cluster) {
+        if (cudaMemsetAsync(w.sweepmax, 0, 64 * sizeof(double), st) != cudaSuccess) return -2;
+        if (cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<8>, A, Jm, rows, ns, gld, nblk_e, tol2, conv, max_sweeps, w.info,
+                               w.sweepmax, w.flags) != cudaSuccess)
+          return -2;
+        nl += 2;
+        if (cudaMemcpyAsync(&hflag, w.flags, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
+        return hflag ? 0 : -5;
+      }
+    }
+  }
   for (int sw = 0; sw < max_sweeps && !hflag; ++sw) {
     if (gram) {
       // one sweep = nblk_e-1 launches + bookkeeping; replayed as a CUDA graph (the launch gaps of

@@ -12,7 +12,7 @@ cap() {  # name regex skip
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -f \
       -o gpurun_out/prof_${TAG}_$1 $B > gpurun_out/ncu_$1.log 2>&1
 }
-cap krgemm krgemm_kernel 231
+cap krgemm2 krgemm2_kernel 231
 cap krgram krgram_kernel 5
 cap fat fat_kernel_t 20
 cap jacobi_gram jacobi_gram 100
