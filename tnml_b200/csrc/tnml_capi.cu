@@ -530,21 +530,37 @@ int fetch(tnml_handle h, const double* dsrc, int n, double* hdst) {
 }
 
 // gradient evaluation at X: G (+16 stats tail, all-reduced), host stats out
-int grad_eval(tnml_handle h, const double* X, double* hstats) {
+// After the all-reduce: G -= lambda*X (fixedL.cc:386,422), |G|^2 into slot 12 of the 16-double tail,
+// then ONE read-back for the cost statistics and the residual norm (each read-back drains the
+// stream: ~15 us of idle GPU, 17 of them per bond update before they were merged).
+int finish_grad(tnml_handle h, const double* X, double lambda, double* hstats) {
+  const long n = h->g.size();
+  if (lambda != 0.0) {
+    axpby(h->st, n, -lambda, X, 1.0, h->G.p);
+    CKL();
+    h->stats.launches += 1;
+  }
+  dot(h->st, n, h->G.p, h->G.p, h->dot_scratch, h->G.p + n + 12);
+  CKL();
+  h->stats.launches += 2;
+  TRY(fetch(h, h->G.p + n, 16, hstats));
+  return 0;
+}
+
+int grad_eval(tnml_handle h, const double* X, double lambda, double* hstats) {
   const long n = h->g.size();
   TRY(ensure(h, h->G, (size_t)n + 16));
   TRY(forward(h, X, FAT_GRAD, h->dscal));
   TRY(backward(h));
   CK(cudaMemcpyAsync(h->G.p + n, h->dscal, 16 * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
   TRY(allreduce(h, h->G.p, (size_t)n + 16));
-  TRY(fetch(h, h->G.p + n, 16, hstats));
-  return 0;
+  return finish_grad(h, X, lambda, hstats);
 }
 
 // cg_reuse_forward: the forward outputs are linear in the bond tensor, P(B + a p) = P(B) + a P(p),
 // and P(p) was just computed for pAp -- so the next residual needs only the backward half:
 // dP = delta - P, cost statistics, Z (one pass over the fat environment) and the krgram contraction.
-int grad_from_P(tnml_handle h, double* hstats) {
+int grad_from_P(tnml_handle h, const double* X, double lambda, double* hstats) {
   const int b = h->currb;
   const BondGeom& g = h->g;
   EnvRef le, re;
@@ -575,8 +591,7 @@ int grad_from_P(tnml_handle h, double* hstats) {
   TRY(backward(h));
   CK(cudaMemcpyAsync(h->G.p + n, h->dscal, 16 * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
   TRY(allreduce(h, h->G.p, (size_t)n + 16));
-  TRY(fetch(h, h->G.p + n, 16, hstats));
-  return 0;
+  return finish_grad(h, X, lambda, hstats);
 }
 
 int ddot(tnml_handle h, long n, const double* x, const double* y, double* out) {
@@ -960,16 +975,10 @@ int tnml_cgrad(tnml_handle h, int Npass, double lambda, double cconv, double* co
   double hs[16];
   int nd = 0;
   // r = sum_n (delta - B v_n) v_n - lambda B     (fixedL.cc:373-386)
-  TRY(grad_eval(h, h->B.p, hs));
+  TRY(grad_eval(h, h->B.p, lambda, hs));              // G = sum_n dP_n v_n - lambda B, hs[12] = |G|^2
   CK(cudaMemcpyAsync(h->r.p, h->G.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
-  if (lambda != 0.0) {
-    axpby(h->st, n, -lambda, h->B.p, 1.0, h->r.p);
-    CKL();
-    h->stats.launches += 1;
-  }
   CK(cudaMemcpyAsync(h->p.p, h->r.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->st));  // p = r (388)
-  double rr = 0.0;
-  TRY(ddot(h, n, h->r.p, h->r.p, &rr));
+  double rr = hs[12];
   for (int pass = 1; pass <= Npass; ++pass) {
     // pAp = sum_n |p v_n|^2 + lambda |p|^2          (393-403)
     TRY(forward(h, h->p.p, FAT_PAP, h->dscal, h->cg_reuse_forward ? h->PV : nullptr));
@@ -990,17 +999,11 @@ int tnml_cgrad(tnml_handle h, int Npass, double lambda, double cconv, double* co
       axpby(h->st, (long)h->NT * NL, a, h->PV, 1.0, h->P);   // P(B + a p) = P(B) + a P(p)
       CKL();
       h->stats.launches += 1;
-      TRY(grad_from_P(h, hs));
+      TRY(grad_from_P(h, h->B.p, lambda, hs));
     } else {
-      TRY(grad_eval(h, h->B.p, hs));                  // 412-421
+      TRY(grad_eval(h, h->B.p, lambda, hs));          // 412-422 (incl. nr -= lambda*B)
     }
-    if (lambda != 0.0) {
-      axpby(h->st, n, -lambda, h->B.p, 1.0, h->G.p);  // 422
-      CKL();
-      h->stats.launches += 1;
-    }
-    double nrr = 0.0;
-    TRY(ddot(h, n, h->G.p, h->G.p, &nrr));
+    const double nrr = hs[12];
     const double beta = nrr / rr;                     // 423
     CK(cudaMemcpyAsync(h->r.p, h->G.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->st));  // 424
     rr = nrr;
@@ -1059,9 +1062,9 @@ int tnml_svd_split(tnml_handle h, int dir, double cutoff, int maxm, int minm, in
   return TNML_OK;
 }
 
-int tnml_quadcost(tnml_handle h, int use_sites, double lambda, double* C, double* C_label, int64_t* ncorrect) {
-  if (!h || h->currb < 1) return h ? fail(h, TNML_ERR_INVALID, "no current bond") : TNML_ERR_INVALID;
-  CK(cudaSetDevice(h->device));
+// quadcost, enqueue half: forward pass + all-reduce of the statistics into dscal[0..15], lambda*|X|^2
+// term into dscal[18].  The caller reads dscal back (one read-back for everything it needs).
+static int quadcost_enqueue(tnml_handle h, int use_sites, double lambda) {
   const double* X;
   if (use_sites) {
     const int b = h->currb;
@@ -1075,22 +1078,33 @@ int tnml_quadcost(tnml_handle h, int use_sites, double lambda, double* C, double
     if (!h->bond_valid) return fail(h, TNML_ERR_INVALID, "no bond tensor formed");
     X = h->B.p;
   }
-  double hs[16];
   TRY(forward(h, X, FAT_COST, h->dscal));
   TRY(allreduce(h, h->dscal, 16));
-  TRY(fetch(h, h->dscal, 16, hs));
+  if (lambda != 0.0) {
+    dot(h->st, h->g.size(), X, X, h->dot_scratch, h->dscal + 18);
+    CKL();
+    h->stats.launches += 2;
+  }
+  return 0;
+}
+static void quadcost_collect(const double* hs, double lambda, double* C, double* C_label, int64_t* ncorrect) {
   double c = 0.0;
   for (int l = 0; l < NL; ++l) {
     c += hs[l];
     if (C_label) C_label[l] = hs[l];
   }
-  if (lambda != 0.0) {
-    double bb = 0.0;
-    TRY(ddot(h, h->g.size(), X, X, &bb));
-    c += lambda * bb;  // fixedL.cc:329
-  }
+  if (lambda != 0.0) c += lambda * hs[18];  // fixedL.cc:329
   if (C) *C = c;
   if (ncorrect) *ncorrect = (int64_t)llround(hs[10]);
+}
+
+int tnml_quadcost(tnml_handle h, int use_sites, double lambda, double* C, double* C_label, int64_t* ncorrect) {
+  if (!h || h->currb < 1) return h ? fail(h, TNML_ERR_INVALID, "no current bond") : TNML_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  TRY(quadcost_enqueue(h, use_sites, lambda));
+  double hs[19];
+  TRY(fetch(h, h->dscal, 19, hs));
+  quadcost_collect(hs, lambda, C, C_label, ncorrect);
   return TNML_OK;
 }
 
@@ -1119,18 +1133,23 @@ int tnml_bond_update(tnml_handle h, int b, int ha, const tnml_bond_params* p, tn
   TRY(tnml_svd_split(h, ha == 1 ? TNML_FROMLEFT : TNML_FROMRIGHT, p->cutoff, p->maxm, p->minm, p->do_rel_cutoff,
                      &res.newm, &res.truncerr));                        // 519-521
   res.svd_sweeps = (int)h->hpin[32];
-  TRY(tnml_quadcost(h, 1, p->lambda, &res.cost, res.cost_label, &res.ncorrect));  // 527-532 (newB in T)
-  // |B|, |B - newB|  (528-530)
-  double bb = 0.0, dd = 0.0;
-  TRY(ddot(h, n, h->B.p, h->B.p, &bb));
+  // quadcost(newB) (527-532, newB in T), |B| and |B - newB| (528-530) and shiftE (540) are all
+  // enqueued before the single read-back of their scalars, so the GPU stays busy while the host waits
+  TRY(quadcost_enqueue(h, 1, p->lambda));
+  dot(h->st, n, h->B.p, h->B.p, h->dot_scratch, h->dscal + 16);
+  CKL();
   axpby(h->st, n, -1.0, h->T.p, 1.0, h->B.p);
   CKL();
-  h->stats.launches += 1;
-  TRY(ddot(h, n, h->B.p, h->B.p, &dd));
-  res.normB = std::sqrt(bb);
-  res.dB = std::sqrt(dd);
+  dot(h->st, n, h->B.p, h->B.p, h->dot_scratch, h->dscal + 17);
+  CKL();
+  h->stats.launches += 5;
   h->bond_valid = false;
   TRY(tnml_shift_env(h, b, ha == 1 ? TNML_FROMLEFT : TNML_FROMRIGHT));  // 540
+  double hs[19];
+  TRY(fetch(h, h->dscal, 19, hs));
+  quadcost_collect(hs, p->lambda, &res.cost, res.cost_label, &res.ncorrect);
+  res.normB = std::sqrt(hs[16]);
+  res.dB = std::sqrt(hs[17]);
   if (out) *out = res;
   return TNML_OK;
 }

@@ -878,6 +878,7 @@ jacobi_cluster_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows,
   }
   if (crank == 0 && tid == 0) {
     info[3] += (double)sweeps_done;
+    info[6] = (double)converged;
     flags[0] = converged;
   }
 }
@@ -1600,9 +1601,7 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
                                cross_only, w.info, w.sweepmax, w.flags) != cudaSuccess)
           return -2;
         nl += 2;
-        if (cudaMemcpyAsync(&hflag, w.flags, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
-        if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
-        return hflag ? 0 : -5;
+        return 1;   // convergence flag is in info[6]: the caller reads it with the truncation results (one sync)
       }
     }
   }
@@ -1829,6 +1828,7 @@ int svd_split(cudaStream_t st, SvdWork& w, const double* Bc, BondGeom g, int dir
   double hinfo[8];
   if (cudaMemcpyAsync(hinfo, w.info, sizeof(hinfo), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
   if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
+  if (rc == 1) rc = (hinfo[6] != 0.0) ? 0 : -5;   // cluster-resident Jacobi: deferred convergence check
   const int m = (int)hinfo[1];
   *newm = m;
   *truncerr = hinfo[2];
