@@ -543,6 +543,8 @@ int finish_grad(tnml_handle h, const double* X, double lambda, double* hstats) {
   dot(h->st, n, h->G.p, h->G.p, h->dot_scratch, h->G.p + n + 12);
   CKL();
   h->stats.launches += 2;
+  // |r|^2 also stays on the device (dscal[20]) for the next step size a = |r|^2 / pAp
+  CK(cudaMemcpyAsync(h->dscal + 20, h->G.p + n + 12, sizeof(double), cudaMemcpyDeviceToDevice, h->st));
   TRY(fetch(h, h->G.p + n, 16, hstats));
   return 0;
 }
@@ -983,20 +985,21 @@ int tnml_cgrad(tnml_handle h, int Npass, double lambda, double cconv, double* co
     // pAp = sum_n |p v_n|^2 + lambda |p|^2          (393-403)
     TRY(forward(h, h->p.p, FAT_PAP, h->dscal, h->cg_reuse_forward ? h->PV : nullptr));
     TRY(allreduce(h, h->dscal, 16));
-    TRY(fetch(h, h->dscal, 16, hs));
-    double pAp = hs[11];
     if (lambda != 0.0) {
-      double pp = 0.0;
-      TRY(ddot(h, n, h->p.p, h->p.p, &pp));
-      pAp += lambda * pp;
+      dot(h->st, n, h->p.p, h->p.p, h->dot_scratch, h->dscal + 21);
+      CKL();
+      h->stats.launches += 2;
     }
-    const double a = rr / pAp;                        // 405
-    axpby(h->st, n, a, h->p.p, 1.0, h->B.p);          // 406
+    // a = |r|^2 / pAp (405) and B += a p (406) on the device: no read-back between the pAp pass and
+    // the next gradient (|r|^2 is in dscal[20] since the last gradient, pAp in dscal[11])
+    cg_step(h->st, h->dscal + 20, h->dscal + 11, lambda, h->dscal + 21, h->dscal + 22);
     CKL();
-    h->stats.launches += 1;
+    axpby_dev(h->st, n, h->dscal + 22, h->p.p, 1.0, h->B.p);
+    CKL();
+    h->stats.launches += 2;
     if (pass == Npass) break;                         // 409
     if (h->cg_reuse_forward) {
-      axpby(h->st, (long)h->NT * NL, a, h->PV, 1.0, h->P);   // P(B + a p) = P(B) + a P(p)
+      axpby_dev(h->st, (long)h->NT * NL, h->dscal + 22, h->PV, 1.0, h->P);   // P(B + a p) = P(B) + a P(p)
       CKL();
       h->stats.launches += 1;
       TRY(grad_from_P(h, h->B.p, lambda, hs));

@@ -933,6 +933,30 @@ void axpby(cudaStream_t st, long n, double a, const double* x, double b, double*
   axpby_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, a, x, b, y);
 }
 
+// y = (*a)*x + b*y with the scalar read from device memory: the CG step size a = |r|^2 / pAp
+// (fixedL.cc:405) never visits the host
+__global__ void axpby_dev_kernel(long n, const double* __restrict__ a_ptr, const double* __restrict__ x, double b,
+                                 double* __restrict__ y) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const double a = *a_ptr;
+  if (i < n) y[i] = fma(a, x[i], b * y[i]);
+}
+void axpby_dev(cudaStream_t st, long n, const double* a_ptr, const double* x, double b, double* y) {
+  if (n <= 0) return;
+  axpby_dev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, a_ptr, x, b, y);
+}
+__global__ void cg_step_kernel(const double* __restrict__ rr, const double* __restrict__ pAp, double lambda,
+                               const double* __restrict__ pp, double* __restrict__ a_out) {
+  if (threadIdx.x == 0) {
+    double d = pAp[0];
+    if (lambda != 0.0) d += lambda * pp[0];
+    a_out[0] = rr[0] / d;
+  }
+}
+void cg_step(cudaStream_t st, const double* rr, const double* pAp, double lambda, const double* pp, double* a_out) {
+  cg_step_kernel<<<1, 32, 0, st>>>(rr, pAp, lambda, pp, a_out);
+}
+
 constexpr int DOT_BLOCKS = 128;
 __global__ void dot_kernel(long n, const double* __restrict__ x, const double* __restrict__ y,
                            double* __restrict__ scratch) {

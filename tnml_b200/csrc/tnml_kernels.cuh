@@ -69,6 +69,9 @@ void permute_site(cudaStream_t st, const double* W, int ma, int mb, int nl, int 
 void fill(cudaStream_t st, double* x, long n, double v);
 // y = a*x + b*y
 void axpby(cudaStream_t st, long n, double a, const double* x, double b, double* y);
+// y = (*a_ptr)*x + b*y ; *a_out = *rr / (*pAp + lambda * *pp)   (CG step of fixedL.cc:405-406 on the device)
+void axpby_dev(cudaStream_t st, long n, const double* a_ptr, const double* x, double b, double* y);
+void cg_step(cudaStream_t st, const double* rr, const double* pAp, double lambda, const double* pp, double* a_out);
 // out[0] = sum x*y (deterministic two-stage)
 void dot(cudaStream_t st, long n, const double* x, const double* y, double* scratch, double* out);
 
