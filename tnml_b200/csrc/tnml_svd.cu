@@ -653,6 +653,11 @@ jacobi_cluster_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows,
   unsigned short* PQc = PQf + NR * W;                                   // [W][W]
   unsigned char* POSf = reinterpret_cast<unsigned char*>(PQc + W * W);  // [NR][NC]
   unsigned char* POSc = POSf + NR * NC;                                 // [W][NC]
+  // look-ahead table: everything the thread that prepares pair j of inner round rd+1 needs
+  // (positions and partners of its two columns in round rd), packed in one word -- one shared-memory
+  // load on the serial chain instead of three dependent ones
+  unsigned* LAf = reinterpret_cast<unsigned*>(POSc + W * NC);           // [NR-1][W]
+  unsigned* LAc = LAf + (NR - 1) * W;                                   // [W-1][W]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int tot = rows + ns;
   const int rows2 = rows >> 1, tot2 = tot >> 1, ld2 = ld >> 1;
@@ -674,6 +679,23 @@ jacobi_cluster_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows,
     POSc[rd * NC + p] = (unsigned char)(2 * k);
     POSc[rd * NC + q] = (unsigned char)(2 * k + 1);
   }
+  __syncthreads();
+  for (int i = tid; i < (NR - 1) * W + (W - 1) * W; i += NTH) {
+    const bool fullm = i < (NR - 1) * W;
+    const int ii = fullm ? i : i - (NR - 1) * W;
+    const int rd = ii / W, j = ii - rd * W;
+    const unsigned short* PQm = fullm ? PQf : PQc;
+    const unsigned char* POSm = fullm ? POSf : POSc;
+    const int pqn = PQm[(rd + 1) * W + j];
+    const int x = pqn & 0xff, y = pqn >> 8;
+    const int ix = POSm[rd * NC + x], iy = POSm[rd * NC + y];
+    const int kx = ix >> 1, ky = iy >> 1;
+    const int pqx = PQm[rd * W + kx], pqy = PQm[rd * W + ky];
+    const unsigned word = (unsigned)(pqx & 0xf) | ((unsigned)((pqx >> 8) & 0xf) << 4) | ((unsigned)(pqy & 0xf) << 8) |
+                          ((unsigned)((pqy >> 8) & 0xf) << 12) | ((unsigned)kx << 16) | ((unsigned)ky << 20) |
+                          ((unsigned)(ix & 1) << 24) | ((unsigned)(iy & 1) << 25);
+    (fullm ? LAf : LAc)[ii] = word;
+  }
   if (active) {
     int P, Q;
     rr_pair(nblk_e, 0, crank, P, Q);
@@ -690,6 +712,28 @@ jacobi_cluster_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows,
   cluster.sync();
 
   int cur = 0, R = 0, sweeps_done = 0, converged = 0;
+  // Per-pairing setup that does not depend on the incoming columns: identity in RA and the
+  // destination (owner CTA, slot) of every local column in the following pairing.  It runs between
+  // barrier.cluster.arrive and .wait of the previous pairing, hidden behind the barrier latency.
+  auto setup_round = [&](int Rcur, int curbuf) {
+    if (!active) return;
+    const int Rnext = (Rcur + 1 == nrd) ? 0 : Rcur + 1;
+    double* Snext = curbuf ? buf0 : buf1;
+    if (tid < NC) {
+      int P, Q;
+      rr_pair(nblk_e, Rcur, crank, P, Q);
+      const int blk = (tid < W) ? P : Q;
+      int k2, slot;
+      rr_where(nblk_e, Rnext, blk, k2, slot);
+      double* remote = cluster.map_shared_rank(Snext, (unsigned)k2);
+      DST[tid] = remote + (long)(slot * W + (tid & (W - 1))) * ld;
+    }
+    for (int i = tid; i < NC * GLD; i += NTH) RA[i] = ((i / GLD) == (i % GLD)) ? 1.0 : 0.0;
+  };
+  setup_round(0, 0);
+  __syncthreads();
+  long long ph[6] = {0, 0, 0, 0, 0, 0};   // TNML_QR_DEBUG: cycles in setup / gram / rounds / apply / cluster barrier
+  const bool prof = (g_qr_dbg != nullptr) && crank == 0 && tid == 0;
   for (int sw = 0; sw < max_sweeps; ++sw) {
     double mo = 0.0;
     for (int rr = 0; rr < nrd; ++rr) {
@@ -697,22 +741,12 @@ jacobi_cluster_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows,
       const bool full = (rr == 0) || !cross_only;
       const int nir = full ? NR : W;                       // inner rounds of this block pairing
       const unsigned short* PQ = full ? PQf : PQc;
-      const unsigned char* POS = full ? POSf : POSc;
+      const unsigned* LA = full ? LAf : LAc;
+      long long c0 = prof ? clock64() : 0, c1 = c0, c2 = c0, c3 = c0;
       if (active) {
         double* S = cur ? buf1 : buf0;
-        double* Sn = cur ? buf0 : buf1;
-        int P, Q;
-        rr_pair(nblk_e, R, crank, P, Q);
-        // destination of every local column in the next round
-        if (tid < NC) {
-          const int blk = (tid < W) ? P : Q;
-          int k2, slot;
-          rr_where(nblk_e, Rn, blk, k2, slot);
-          double* remote = cluster.map_shared_rank(Sn, (unsigned)k2);
-          DST[tid] = remote + (long)(slot * W + (tid & (W - 1))) * ld;
-        }
-        for (int i = tid; i < NC * GLD; i += NTH) RA[i] = ((i / GLD) == (i % GLD)) ? 1.0 : 0.0;
         // ---- Gram (rows split over two warps per tile, 4 accumulator chains)
+        if (prof) c1 = clock64();
         {
           const int tile = warp % (TG * TG), kh = warp / (TG * TG);
           const int ti = tile / TG, tj = tile - ti * TG;
@@ -748,6 +782,7 @@ jacobi_cluster_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows,
         }
         __syncthreads();
         // ---- rotation rounds on the Gram matrix (identical to jacobi_gram_kernel)
+        if (prof) c2 = clock64();
         double* curG = G0;
         double* nxtG = G1;
         if (tid < W) {
@@ -793,15 +828,13 @@ jacobi_cluster_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows,
             }
           } else if (tid >= NTH - W && rd + 1 < nir) {
             const int j = tid - (NTH - W);
-            const int pqn = PQ[(rd + 1) * W + j];
-            const int x = pqn & 0xff, y = pqn >> 8;
-            const int ix = POS[rd * NC + x], iy = POS[rd * NC + y];
-            const int kx = ix >> 1, ky = iy >> 1;
-            const int pqx = pqr[kx], pqy = pqr[ky];
-            const int xp = pqx & 0xff, xq = pqx >> 8, yp = pqy & 0xff, yq = pqy >> 8;
+            const unsigned la = LA[rd * W + j];
+            const int xp = la & 0xf, xq = (la >> 4) & 0xf, yp = (la >> 8) & 0xf, yq = (la >> 12) & 0xf;
+            const int kx = (la >> 16) & 0xf, ky = (la >> 20) & 0xf;
+            const bool px = (la >> 24) & 1, py = (la >> 25) & 1;
             const double cx = cs[2 * kx], sx = cs[2 * kx + 1], cy = cs[2 * ky], sy = cs[2 * ky + 1];
-            const double ux = (ix & 1) ? sx : cx, vx = (ix & 1) ? cx : -sx;
-            const double uy = (iy & 1) ? sy : cy, vy = (iy & 1) ? cy : -sy;
+            const double ux = px ? sx : cx, vx = px ? cx : -sx;
+            const double uy = py ? sy : cy, vy = py ? cy : -sy;
             auto quad = [&](int ap, int aq, double ua, double va, int bp, int bq, double ub, double vb) {
               const double g00 = curG[ap * GLD + bp], g01 = curG[ap * GLD + bq];
               const double g10 = curG[aq * GLD + bp], g11 = curG[aq * GLD + bq];
@@ -822,6 +855,7 @@ jacobi_cluster_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows,
           nxtG = tmp;
         }
         // ---- apply the accumulated rotation; the result goes straight to the next round's owners
+        if (prof) c3 = clock64();
         const int nrb = (tot + 7) / 8;
         for (int rb = warp; rb < nrb; rb += NWARP) {
           const int r0 = rb * 8;
@@ -844,7 +878,22 @@ jacobi_cluster_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows,
           }
         }
       }
-      cluster.sync();   // every column of the next round has arrived; this round's buffer is free
+      const long long c4 = prof ? clock64() : 0;
+      // every column of the next pairing must have arrived and this pairing's buffer must be free:
+      // split barrier, the next pairing's setup runs in its shadow
+      __syncthreads();                       // all warps of this CTA are done with RA / DST / S
+      cluster.barrier_arrive();
+      setup_round(Rn, cur ^ 1);
+      cluster.barrier_wait();
+      if (prof) {
+        const long long c5 = clock64();
+        ph[0] += c1 - c0;
+        ph[1] += c2 - c1;
+        ph[2] += c3 - c2;
+        ph[3] += c4 - c3;
+        ph[4] += c5 - c4;
+        ph[5] += 1;
+      }
       cur ^= 1;
       R = Rn;
     }
@@ -876,6 +925,8 @@ jacobi_cluster_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows,
       }
     }
   }
+  if (prof)
+    for (int i = 0; i < 6; ++i) g_qr_dbg[2064 + i] = ph[i];
   if (crank == 0 && tid == 0) {
     info[3] += (double)sweeps_done;
     info[6] = (double)converged;
@@ -1567,7 +1618,8 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
   }
   if (gram && use_cluster && GW == 8 && nblk_e <= 32) {
     const size_t need_cl = ((size_t)2 * 16 * gld + 3 * 16 * GLD + 4 * 8) * sizeof(double) + 16 * sizeof(double*) +
-                           (size_t)(15 + 8) * 8 * sizeof(unsigned short) + (size_t)(15 + 8) * 16 + 16;
+                           (size_t)(15 + 8) * 8 * sizeof(unsigned short) + (size_t)(15 + 8) * 16 +
+                           (size_t)(14 + 7) * 8 * sizeof(unsigned) + 32;
     if (need_cl <= 220 * 1024) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(16, 1, 1);
@@ -1728,8 +1780,12 @@ static void launch_qr_block8(cudaStream_t st, SvdWork& w, double* Xq, double* ta
       if (fg) {
         fprintf(fg, "gram kernel phases (cycles): stage %lld gram %lld rounds %lld apply %lld store %lld\n", gs[1] - gs[0],
                 gs[2] - gs[1], gs[3] - gs[2], gs[4] - gs[3], gs[5] - gs[4]);
-        fprintf(fg, "round 3 (thread 0): rot %lld  bar1 %lld  update %lld  bar2 %lld\n", rs[1] - rs[0], rs[2] - rs[1],
-                rs[3] - rs[2], rs[4] - rs[3]);
+        long long cs[6];
+        cudaMemcpy(cs, dbg + 2064, sizeof(cs), cudaMemcpyDeviceToHost);
+        if (cs[5] > 0)
+          fprintf(fg, "cluster kernel, CTA 0, cycles per block pairing over %lld pairings: setup %lld gram %lld rounds %lld "
+                      "apply %lld cluster barrier %lld\n", cs[5], cs[0] / cs[5], cs[1] / cs[5], cs[2] / cs[5], cs[3] / cs[5],
+                  cs[4] / cs[5]);
         fclose(fg);
       }
     }
