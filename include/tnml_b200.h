@@ -178,7 +178,11 @@ int tnml_comm_init_rank(tnml_handle h, int nranks, int rank, const uint8_t* id);
  * needs (fixedL.cc:177-178); here at most this many GiB of environment slots stay in HBM, the rest
  * lives in pinned host memory.  Slots are evicted farthest-next-use first and the slot the next
  * bond needs is fetched on a copy stream while the current bond computes.  Results are bit-identical
- * to the all-resident run. */
+ * to the all-resident run.
+ * Process-wide variant switches for tests and A/B timing (-1 restores the default):
+ * "krgemm_variant" (1: register-staged projection kernel only), "svd_cluster" (0: multi-launch Jacobi
+ * instead of the cluster-resident kernel), "svd_cross" (0: full inner tournaments), "svd_precond"
+ * (0: plain Jacobi, 1: one QR, 3: column sort + two QRs). */
 int tnml_set_option(tnml_handle h, const char* name, double value);
 
 /* Counters for the roofline report: kernel launches issued by this library,

@@ -313,6 +313,42 @@ def test_krgemm_variants_agree(capi, m0, NT):
         ts.shiftE(W, b, "Fromleft")
 
 
+def test_svd_variants_agree(capi):
+    """The SVD variants (cluster-resident Jacobi with cross-only inner tournaments = default; full
+    tournaments; multi-launch Jacobi; one QR instead of sort + two QRs; no preconditioner) give the
+    same truncated factorisation: same m, same truncation error, same U*S*V to 1e-11, isometry."""
+    feat, labels, W = make_problem(N=16, NT=64, m0=20)
+    h = _gpu_state(capi, feat, labels, W)
+    for bb in range(1, 8):
+        h.set_bond(bb)
+        h.shift_env(bb, capi.FROMLEFT)
+    h.set_bond(8)
+    rng = np.random.default_rng(3)
+    B0 = O.form_bond(W[8], W[9])
+    B = B0 + 1e-4 * np.linalg.norm(B0) / np.sqrt(B0.size) * rng.standard_normal(B0.shape)
+    variants = [dict(), dict(svd_cross=0), dict(svd_cluster=0), dict(svd_precond=1), dict(svd_precond=0, svd_cluster=0)]
+    outs = []
+    for v in variants:
+        for k2, val in v.items():
+            h.set_option(k2, val)
+        h.bond_load(B)
+        m, te = h.svd_split(capi.FROMLEFT, 1e-10, 20, 10)
+        Wb, Wb1 = h.get_site(8), h.get_site(9)
+        outs.append((m, te, O.form_bond(Wb, Wb1), Wb))
+        for k2 in v:
+            h.set_option(k2, -1)
+    m0, te0, nb0, _ = outs[0]
+    Wo, Wo1, mo, teo = O.svd_split(B, 8, 1, 8, 20, 10, 1e-10)
+    assert m0 == mo and abs(te0 - teo) <= 1e-8 * teo + 1e-22
+    assert rel(nb0, O.form_bond(Wo, Wo1)) < 1e-10
+    for m, te, nb, Wb in outs:
+        assert m == m0 and abs(te - te0) <= 1e-8 * te0 + 1e-22
+        assert rel(nb, nb0) < 1e-11
+        U = Wb.reshape(-1, m)
+        assert np.abs(U.T @ U - np.eye(m)).max() < 1e-10
+    h.close()
+
+
 def test_env_tier_bit_identical(capi):
     """environment tiering.  With an HBM budget that holds only a handful of
     environment slots (the rest live in pinned host memory, fetched ahead on a copy stream) two

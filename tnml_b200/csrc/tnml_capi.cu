@@ -1228,6 +1228,10 @@ int tnml_set_option(tnml_handle h, const char* name, double value) {
     h->cg_reuse_forward = (value != 0.0);
     return TNML_OK;
   }
+  if (strcmp(name, "svd_cluster") == 0 || strcmp(name, "svd_cross") == 0 || strcmp(name, "svd_precond") == 0) {
+    svd_set_variant(name, (int)value);          // process-wide (testing / A-B timing)
+    return TNML_OK;
+  }
   if (strcmp(name, "krgemm_variant") == 0) {   // process-wide (testing / A-B timing)
     krgemm_set_variant((int)value);
     return TNML_OK;

@@ -109,6 +109,9 @@ struct SvdWork {
   long gstamp[NGRAPH] = {};
   long gclock = 0;
 };
+// variant switches for tests / A-B timing: "svd_cluster" (0: multi-launch Jacobi), "svd_cross" (0: full
+// inner tournaments), "svd_precond" (1: one QR, 3: column sort + two QRs, 0: none)
+void svd_set_variant(const char* what, int v);
 // Gather canonical B into X (tall orientation), run block one-sided Jacobi,
 // sort, apply ITensor's truncation rule, scatter U -> W(c), S*V -> W(c+dc).
 // dir = 1: rows are (alpha,s[,l]) ; dir = 2: rows are (t,beta[,l]).

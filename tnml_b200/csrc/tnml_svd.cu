@@ -26,6 +26,15 @@ namespace tnml {
 
 constexpr int JW = 16;  // block width (columns)
 
+// process-wide variant switches (tnml_set_option "svd_cluster" / "svd_cross" / "svd_precond"; -1 = take
+// the TNML_SVD_* environment variable or the default).  Testing and A/B timing only.
+static int g_svd_cluster = -1, g_svd_cross = -1, g_svd_precond = -1;
+void svd_set_variant(const char* what, int v) {
+  if (what[4] == 'c' && what[5] == 'l') g_svd_cluster = v;        // svd_cluster
+  else if (what[4] == 'c' && what[5] == 'r') g_svd_cross = v;     // svd_cross
+  else g_svd_precond = v;                                          // svd_precond: 1 one QR, 3 sort + two QRs
+}
+
 __device__ long long* g_qr_dbg = nullptr;   // optional [ns][4] clock64 stamps (TNML_QR_DEBUG)
 
 
@@ -1616,7 +1625,8 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
       }
     }
   }
-  if (gram && use_cluster && GW == 8 && nblk_e <= 32) {
+  const bool want_cluster = (g_svd_cluster >= 0) ? (g_svd_cluster != 0 && use_cluster >= 0 && use_cluster != 0) : (use_cluster != 0);
+  if (gram && want_cluster && GW == 8 && nblk_e <= 32) {
     const size_t need_cl = ((size_t)2 * 16 * gld + 3 * 16 * GLD + 4 * 8) * sizeof(double) + 16 * sizeof(double*) +
                            (size_t)(15 + 8) * 8 * sizeof(unsigned short) + (size_t)(15 + 8) * 16 +
                            (size_t)(14 + 7) * 8 * sizeof(unsigned) + 32;
@@ -1649,8 +1659,9 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
           const char* e = getenv("TNML_SVD_CROSS");
           cross_only = e ? atoi(e) : 1;
         }
+        const int cross_now = (g_svd_cross >= 0) ? g_svd_cross : cross_only;
         if (cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<8>, A, Jm, rows, ns, gld, nblk_e, tol2, conv, max_sweeps,
-                               cross_only, w.info, w.sweepmax, w.flags) != cudaSuccess)
+                               cross_now, w.info, w.sweepmax, w.flags) != cudaSuccess)
           return -2;
         nl += 2;
         return 1;   // convergence flag is in info[6]: the caller reads it with the truncation results (one sync)
@@ -1842,14 +1853,15 @@ int svd_split(cudaStream_t st, SvdWork& w, const double* Bc, BondGeom g, int dir
   }
   // QR preconditioning pays off from a few dozen columns on; it needs one resident warp per
   // column and the column in registers (nb <= 32*96)
-  const bool qr = (w.use_qr == 1 || w.use_qr == 3 || (w.use_qr == 2 && ns >= 32)) && nb <= 32 * 96 && ns <= 8 * 140;
+  const int use_qr = (g_svd_precond >= 0) ? g_svd_precond : w.use_qr;
+  const bool qr = (use_qr == 1 || use_qr == 3 || (use_qr == 2 && ns >= 32)) && nb <= 32 * 96 && ns <= 8 * 140;
 
   long nJ = (long)ns * ns;
   long ninit = nJ > 8 ? nJ : 8;
   long nX = (long)nb * ns;
   // 3 = column sort + two QRs (X P0 = Q1 R1, R1^T = Q2 R2, Jacobi on R2^T): about half the Jacobi
   // sweeps of the one-QR path on freshly optimised bond matrices (tools/jacobi_precond_study.py)
-  const bool qr2 = qr && (w.use_qr == 2 || w.use_qr == 3);
+  const bool qr2 = qr && (use_qr == 2 || use_qr == 3);
   svd_init_kernel<<<(unsigned)((ninit + 255) / 256), 256, 0, st>>>(w.J, ns, w.info, w.flags);
   nl += 1;
   int rc;

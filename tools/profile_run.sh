@@ -6,7 +6,7 @@
 TAG=${1:-r01}
 mkdir -p gpurun_out
 B="python bench.py --steps 4 --warmup 3 --nt 30000 --no-cpu-baseline"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 1200 -c 2100 --csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 700 --csv \
     --log-file gpurun_out/launches_${TAG}.csv $B > gpurun_out/ncu_ll.log 2>&1
 cap() {  # name regex skip
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -f \
@@ -15,6 +15,6 @@ cap() {  # name regex skip
 cap krgemm2 krgemm2_kernel 231
 cap krgram krgram_kernel 5
 cap fat fat_kernel_t 20
-cap jacobi_gram jacobi_gram 100
+cap jacobi_cluster jacobi_cluster_kernel 5
 cap qr_block qr_block_kernel 3
 ls -la gpurun_out/*.ncu-rep
