@@ -319,12 +319,13 @@ def test_svd_variants_agree(capi):
     same truncated factorisation: same m, same truncation error, same U*S*V to 1e-11, isometry."""
     feat, labels, W = make_problem(N=16, NT=64, m0=20)
     h = _gpu_state(capi, feat, labels, W)
-    for bb in range(1, 8):
+    b = 6                                   # class-L bond, 40 x 40 bond matrix (label site is 8)
+    for bb in range(1, b):
         h.set_bond(bb)
         h.shift_env(bb, capi.FROMLEFT)
-    h.set_bond(8)
+    h.set_bond(b)
     rng = np.random.default_rng(3)
-    B0 = O.form_bond(W[8], W[9])
+    B0 = O.form_bond(W[b], W[b + 1])
     B = B0 + 1e-4 * np.linalg.norm(B0) / np.sqrt(B0.size) * rng.standard_normal(B0.shape)
     variants = [dict(), dict(svd_cross=0), dict(svd_cluster=0), dict(svd_precond=1), dict(svd_precond=0, svd_cluster=0)]
     outs = []
@@ -333,12 +334,12 @@ def test_svd_variants_agree(capi):
             h.set_option(k2, val)
         h.bond_load(B)
         m, te = h.svd_split(capi.FROMLEFT, 1e-10, 20, 10)
-        Wb, Wb1 = h.get_site(8), h.get_site(9)
+        Wb, Wb1 = h.get_site(b), h.get_site(b + 1)
         outs.append((m, te, O.form_bond(Wb, Wb1), Wb))
         for k2 in v:
             h.set_option(k2, -1)
     m0, te0, nb0, _ = outs[0]
-    Wo, Wo1, mo, teo = O.svd_split(B, 8, 1, 8, 20, 10, 1e-10)
+    Wo, Wo1, mo, teo = O.svd_split(B, b, 1, 8, 20, 10, 1e-10)
     assert m0 == mo and abs(te0 - teo) <= 1e-8 * teo + 1e-22
     assert rel(nb0, O.form_bond(Wo, Wo1)) < 1e-10
     for m, te, nb, Wb in outs:
