@@ -575,6 +575,132 @@ krgram_kernel(const double* __restrict__ In, long ldin, int ma, const double* __
   }
 }
 
+// ---------------------------------------------------------------------------
+// krgram2: the same split-K contraction with RAW operand tiles.  The environment slice In, the
+// back-propagated Z and the two feature pairs of 16 images are staged by cp.async, three stages
+// deep; the Khatri-Rao weight w_p(n) = f1[n][p>>1] * f2[n][p&1] is applied when the A fragment is
+// loaded (one DMUL per fragment element: the warp's 16 rows of the tile belong to one p).
+// Removes from krgram_kernel the register-staged loads (18 % long-scoreboard stalls in the ncu
+// capture), the DMUL -> STS chain in front of every barrier and 4x of the shared-memory stores.
+constexpr int R2_BK = 16;      // images per stage
+constexpr int R2_AM = 32;      // a-values per M tile (x 4 weights = 128 rows)
+constexpr int R2_ALD = 36;     // padded In row: 8t + 2g bank pattern, conflict-free per half warp
+constexpr int R2_ZLD = 68;     // padded Z row
+constexpr int R2_STAGES = 3;
+constexpr int R2_STAGE_DOUBLES = R2_BK * (R2_ALD + R2_ZLD + 4);
+
+__global__ void __launch_bounds__(NTHR, 2)
+krgram2_kernel(const double* __restrict__ In, long ldin, int ma, const double* __restrict__ f1,
+               const double* __restrict__ f2, const double* __restrict__ Z, long ldz, int J,
+               double* __restrict__ Gpart, long rows, long rows_per_split, int vecA, int vecZ) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int S = 4;
+  const int t = threadIdx.x;
+  const int lane = t & 31, wm = t >> 5, g = lane >> 2, tq = lane & 3;
+  const int a0 = blockIdx.x * R2_AM;
+  const int j0 = blockIdx.y * BN;
+  const long rbeg = (long)blockIdx.z * rows_per_split;
+  const long rend = (rbeg + rows_per_split < rows) ? (rbeg + rows_per_split) : rows;
+  const long nrow = (rend > rbeg) ? (rend - rbeg) : 0;
+  const int nk = (int)((nrow + R2_BK - 1) / R2_BK);
+
+  auto issue = [&](int kt) {
+    double* As = smem + (long)(kt % R2_STAGES) * R2_STAGE_DOUBLES;   // [16][R2_ALD]
+    double* Zs = As + R2_BK * R2_ALD;                                // [16][R2_ZLD]
+    double* Fs = Zs + R2_BK * R2_ZLD;                                // [16][4] = f1[n][0..1], f2[n][0..1]
+    const long r0 = rbeg + (long)kt * R2_BK;
+    if (vecA) {
+      const int lr = t >> 4, q = 2 * (t & 15), a = a0 + q;
+      const bool ok = (r0 + lr < rend) && (a < ma);
+      cp_async16(As + lr * R2_ALD + q, ok ? (In + (r0 + lr) * ldin + a) : In, ok ? ((ma - a >= 2) ? 16 : 8) : 0);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = t + i * NTHR, lr = c >> 5, q = c & 31, a = a0 + q;
+        const bool ok = (r0 + lr < rend) && (a < ma);
+        cp_async8(As + lr * R2_ALD + q, ok ? (In + (r0 + lr) * ldin + a) : In, ok ? 8 : 0);
+      }
+    }
+    if (vecZ) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = t + i * NTHR, lr = c >> 5, q = 2 * (c & 31), j = j0 + q;
+        const bool ok = (r0 + lr < rend) && (j < J);
+        cp_async16(Zs + lr * R2_ZLD + q, ok ? (Z + (r0 + lr) * ldz + j) : Z, ok ? ((J - j >= 2) ? 16 : 8) : 0);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = t + i * NTHR, lr = c >> 6, q = c & 63, j = j0 + q;
+        const bool ok = (r0 + lr < rend) && (j < J);
+        cp_async8(Zs + lr * R2_ZLD + q, ok ? (Z + (r0 + lr) * ldz + j) : Z, ok ? 8 : 0);
+      }
+    }
+    if (t < 2 * R2_BK) {
+      const int lr = t & (R2_BK - 1);
+      const double* f = (t < R2_BK) ? f1 : f2;
+      const bool ok = (r0 + lr < rend);
+      cp_async16(Fs + lr * 4 + ((t < R2_BK) ? 0 : 2), ok ? (f + (r0 + lr) * 2) : f, ok ? 16 : 0);
+    }
+  };
+
+  double acc[2][8][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+  for (int s0 = 0; s0 < R2_STAGES - 1; ++s0) {
+    if (s0 < nk) issue(s0);
+    cp_async_commit();
+  }
+  const int pp = wm >> 1;                          // weight index of this warp's 16 rows
+  const int fs_off = pp >> 1, fq_off = 2 + (pp & 1);
+  const int arow = (wm & 1) * 16 + g;              // a-value (within the tile) of fragment row g
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<R2_STAGES - 2>();
+    __syncthreads();
+    if (kt + R2_STAGES - 1 < nk) issue(kt + R2_STAGES - 1);
+    cp_async_commit();
+    const double* As = smem + (long)(kt % R2_STAGES) * R2_STAGE_DOUBLES;
+    const double* Zs = As + R2_BK * R2_ALD;
+    const double* Fs = Zs + R2_BK * R2_ZLD;
+#pragma unroll
+    for (int k4 = 0; k4 < R2_BK / 4; ++k4) {
+      const int n = k4 * 4 + tq;
+      const double w = Fs[n * 4 + fs_off] * Fs[n * 4 + fq_off];
+      double af[2], bf[8];
+      af[0] = As[n * R2_ALD + arow] * w;
+      af[1] = As[n * R2_ALD + arow + 8] * w;
+      const double* bp = Zs + n * R2_ZLD + g;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bf[i] = bp[i * 8];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+    }
+  }
+  cp_async_wait<0>();
+  const long M2 = (long)S * ma;
+  double* Gp = Gpart + (long)blockIdx.z * (M2 * J);
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi) {
+    const int al = (wm & 1) * 16 + mi * 8 + g;
+    if (a0 + al >= ma) continue;
+    const long m2 = (long)(a0 + al) * S + pp;
+#pragma unroll
+    for (int ni = 0; ni < 8; ++ni) {
+      const int j = j0 + ni * 8 + 2 * tq;
+      if (j < J) Gp[m2 * J + j] = acc[mi][ni][0];
+      if (j + 1 < J) Gp[m2 * J + j + 1] = acc[mi][ni][1];
+    }
+  }
+}
+
+static int g_krgram_variant = -1;
+void krgram_set_variant(int v) { g_krgram_variant = v; }
+
 int krgram_splits(int ma, int S, int J, long rows, int num_sm) {
   int mt = (S * ma + BM - 1) / BM, nt = (J + BN - 1) / BN;
   long tiles = (long)mt * nt;
@@ -598,6 +724,22 @@ void krgram(cudaStream_t st, int S, const double* In, long ldin, int ma, const d
     cudaFuncSetAttribute(krgram_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(krgram_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr = true;
+  }
+  if (g_krgram_variant < 0) {   // TNML_KRGRAM=1: register-staged kernel only
+    const char* e = getenv("TNML_KRGRAM");
+    g_krgram_variant = e ? atoi(e) : 2;
+  }
+  if (S == 4 && g_krgram_variant == 2) {
+    static bool attr2 = false;
+    const size_t sh2 = (size_t)R2_STAGES * R2_STAGE_DOUBLES * sizeof(double);
+    if (!attr2) {
+      cudaFuncSetAttribute(krgram2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      attr2 = true;
+    }
+    const int vecA = ((ldin & 1) == 0 && (((size_t)In) & 15) == 0) ? 1 : 0;
+    const int vecZ = ((ldz & 1) == 0 && (((size_t)Z) & 15) == 0) ? 1 : 0;
+    krgram2_kernel<<<grid, NTHR, sh2, st>>>(In, ldin, ma, f1, f2, Z, ldz, J, Gpart, rows, rps, vecA, vecZ);
+    return;
   }
   if (S == 2)
     krgram_kernel<2><<<grid, NTHR, sh, st>>>(In, ldin, ma, f1, f2, Z, ldz, J, Gpart, rows, rps);

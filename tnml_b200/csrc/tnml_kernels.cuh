@@ -28,6 +28,8 @@ void krgemm_set_variant(int v);
 int krgram_splits(int ma, int S, int J, long rows, int num_sm);
 void krgram(cudaStream_t st, int S, const double* In, long ldin, int ma, const double* f1, const double* f2,
             const double* Z, long ldz, int J, double* Gpart, long rows, int nsplit);
+// 2 (default): cp.async-staged raw tiles, weights applied at fragment load; 1: register-staged kernel
+void krgram_set_variant(int v);
 // G[i] = sum_split Gpart[split][i]   (+ optional: G[i] -= lambda*B[i])
 void reduce_partials(cudaStream_t st, const double* Gpart, int nsplit, long n, double* G);
 
