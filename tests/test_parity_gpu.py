@@ -313,6 +313,43 @@ def test_krgemm_variants_agree(capi, m0, NT):
         ts.shiftE(W, b, "Fromleft")
 
 
+def test_fat_and_krgram_variants_agree(capi):
+    """The bulk-async-copy (TMA) label-environment kernel and the cp.async gradient kernel against
+    their register-staged predecessors: one bond update on a class-L, a class-C and a class-R
+    bond gives the same CG costs, link dimension and cost to ~1e-10 (single step, before the
+    chaotic amplification sets in), and both match the oracle.  (The bulk-copy kernel is not the
+    default: it streams at 4.8 TB/s against 5.1 TB/s for the register-resident one.)"""
+    feat, labels, W = make_problem(N=12, NT=1500, m0=6)
+    p = capi.BondParams(3, 1e-5, 1e-10, 1e-10, 12, 6, 0)
+    for b in (3, 5, 8):
+        res = {}
+        for variant in (1, 2):
+            h = _gpu_state(capi, feat, labels, W)
+            h.set_option("fat_variant", variant)
+            h.set_option("krgram_variant", variant)
+            for bb in range(1, b):
+                h.set_bond(bb)
+                h.shift_env(bb, capi.FROMLEFT)
+            r = h.bond_update(b, 1, p)
+            res[variant] = (r.cost, r.newm, r.ncorrect, list(r.cg_cost[:r.npass_done]))
+            h.set_option("fat_variant", 1)
+            h.set_option("krgram_variant", 2)
+            h.close()
+        (c1, m1, n1, g1), (c2, m2, n2, g2) = res[1], res[2]
+        assert m1 == m2 and abs(n1 - n2) <= 1
+        assert abs(c1 - c2) <= 1e-9 * abs(c1)
+        assert np.allclose(g1, g2, rtol=1e-9, atol=0)
+        ts = O.TrainStates(feat, labels)
+        Wc = copy_mps(W)
+        ts.init(Wc)
+        for bb in range(1, b):
+            ts.set_bond(bb)
+            ts.shiftE(Wc, bb, "Fromleft")
+        ts.set_bond(b)
+        Bo, costs, _ = O.cgrad(O.form_bond(Wc[b], Wc[b + 1]), ts, 3, 1e-5)
+        assert np.allclose(g2, costs, rtol=1e-8, atol=0)
+
+
 def test_svd_variants_agree(capi):
     """The SVD variants (cluster-resident Jacobi with cross-only inner tournaments = default; full
     tournaments; multi-launch Jacobi; one QR instead of sort + two QRs; no preconditioner) give the

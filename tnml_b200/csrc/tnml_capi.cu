@@ -1232,6 +1232,10 @@ int tnml_set_option(tnml_handle h, const char* name, double value) {
     svd_set_variant(name, (int)value);          // process-wide (testing / A-B timing)
     return TNML_OK;
   }
+  if (strcmp(name, "fat_variant") == 0) {
+    fat_set_variant((int)value);
+    return TNML_OK;
+  }
   if (strcmp(name, "krgram_variant") == 0) {
     krgram_set_variant((int)value);
     return TNML_OK;

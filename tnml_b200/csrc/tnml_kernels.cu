@@ -917,6 +917,210 @@ fat_kernel_t(const double* __restrict__ Q, const double* __restrict__ F, int m,
   }
 }
 
+// ---------------------------------------------------------------------------
+// fat_bulk_kernel: the same per-image work with the label-carrying environment of an image
+// (NL x m doubles = 9.6 KB at m = 120, contiguous in HBM) brought in by ONE bulk asynchronous copy
+// (TMA, cp.async.bulk ... mbarrier::complete_tx) into a warp-private double buffer in shared
+// memory: the next image's 9.6 KB are in flight while the warp works on the current one, no
+// registers are tied up by the loads, and the number of resident warps is set by shared memory
+// (11 warps x 2 x 9.6 KB at m = 120) instead of by the 168 registers of fat_kernel_t.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(512, 1)
+fat_bulk_kernel(const double* __restrict__ Q, const double* __restrict__ F, int m,
+                const int32_t* __restrict__ labels, double* __restrict__ P, double* __restrict__ Z,
+                int32_t* __restrict__ pred, double* __restrict__ stats_partial, int nblocks_stats, long NT) {
+  constexpr bool GIVEN_P = (MODE == FAT_BWD);
+  constexpr bool DO_Z = (MODE == FAT_GRAD || MODE == FAT_BWD);
+  constexpr int C = 4;                       // m <= 128
+  constexpr int NBUF = 2;                    // ring of NBUF buffers per warp: NBUF-1 images in flight
+  extern __shared__ __align__(128) unsigned char smraw[];
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smraw);     // [16 warps][NBUF] (<= 512 B)
+  double* red = reinterpret_cast<double*>(smraw + 512);                        // [16][12]
+  double* bufs = reinterpret_cast<double*>(smraw + 512 + 16 * 12 * sizeof(double));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int bufd = NL * m;
+  const unsigned bytes = (unsigned)bufd * sizeof(double);
+  double* mybuf = bufs + (long)warp * NBUF * bufd;
+  const unsigned bar0 = smem_u32(bars + warp * NBUF);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NBUF; ++i) mbar_init(bar0 + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long gw = (long)blockIdx.x * wpb + warp;
+  const long nw = (long)gridDim.x * wpb;
+  auto issue = [&](long n, int b) {
+    if (lane == 0) {
+      mbar_expect_tx(bar0 + 8 * b, bytes);
+      bulk_g2s(mybuf + (long)b * bufd, F + n * (long)bufd, bytes, bar0 + 8 * b);
+    }
+  };
+  double cst[NL];
+#pragma unroll
+  for (int l = 0; l < NL; ++l) cst[l] = 0.0;
+  double ncor = 0.0, pap = 0.0;
+#pragma unroll
+  for (int i = 0; i < NBUF - 1; ++i)
+    if (gw + i * nw < NT) issue(gw + i * nw, i);
+  int it = 0, b = 0;
+  unsigned par = 0;
+  for (long n = gw; n < NT; n += nw, ++it) {
+    __syncwarp();                               // every lane is done reading the buffer of iteration it-1
+    {
+      const int bn = (b == 0) ? (NBUF - 1) : (b - 1);   // = (it + NBUF - 1) % NBUF: freed by iteration it-1
+      if (n + (NBUF - 1) * nw < NT) issue(n + (NBUF - 1) * nw, bn);
+    }
+    double qv[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int f = lane + 32 * c;
+      qv[c] = (!GIVEN_P && f < m) ? Q[n * m + f] : 0.0;
+    }
+    double pl[NL];
+    if (GIVEN_P) {
+#pragma unroll
+      for (int l = 0; l < NL; ++l) pl[l] = P[n * NL + l];
+    }
+    const int lab = (MODE == FAT_PAP) ? 0 : labels[n];
+    mbar_wait(bar0 + 8 * b, par);
+    const double* Fn = mybuf + (long)b * bufd;
+    if (!GIVEN_P) {
+#pragma unroll
+      for (int l = 0; l < NL; ++l) pl[l] = 0.0;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int f = lane + 32 * c;
+        if (f < m) {
+#pragma unroll
+          for (int l = 0; l < NL; ++l) pl[l] = fma(qv[c], Fn[l * m + f], pl[l]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int l = 0; l < NL; ++l) pl[l] += __shfl_xor_sync(0xffffffffu, pl[l], o);
+      }
+      if (P != nullptr) {
+        double mine = 0.0;
+#pragma unroll
+        for (int l = 0; l < NL; ++l) mine = (lane == l) ? pl[l] : mine;
+        if (lane < NL) P[n * NL + lane] = mine;
+      }
+    }
+    if (MODE == FAT_PAP) {
+#pragma unroll
+      for (int l = 0; l < NL; ++l) pap = fma(pl[l], pl[l], pap);
+    } else {
+      int am = 0;
+      double mx = fabs(pl[0]);
+#pragma unroll
+      for (int l = 1; l < NL; ++l) {
+        double w = fabs(pl[l]);
+        if (w > mx) {  // first strict maximum, util.h:42-57
+          mx = w;
+          am = l;
+        }
+      }
+      ncor += (am == lab) ? 1.0 : 0.0;
+      if (pred != nullptr && lane == 0) pred[n] = am;
+      double dp[NL];
+      double e = 0.0;
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        dp[l] = ((l == lab) ? 1.0 : 0.0) - pl[l];
+        e = fma(dp[l], dp[l], e);
+      }
+#pragma unroll
+      for (int l = 0; l < NL; ++l) cst[l] += (l == lab) ? e : 0.0;
+      if (DO_Z) {
+        double* z = Z + n * m;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const int f = lane + 32 * c;
+          if (f < m) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int l = 0; l < NL; ++l) sacc = fma(dp[l], Fn[l * m + f], sacc);
+            z[f] = sacc;
+          }
+        }
+      }
+    }
+    if (++b == NBUF) {
+      b = 0;
+      par ^= 1;
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int l = 0; l < NL; ++l) red[warp * 12 + l] = cst[l];
+    red[warp * 12 + 10] = ncor;
+    red[warp * 12 + 11] = pap;
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    double s = 0.0;
+    if (threadIdx.x < 12)
+      for (int w = 0; w < wpb; ++w) s += red[w * 12 + threadIdx.x];
+    stats_partial[(long)blockIdx.x * 16 + threadIdx.x] = s;
+  }
+  // the statistics reducer sums nblocks_stats partials: clear the ones this grid does not own
+  for (long i = (long)gridDim.x * 16 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < (long)nblocks_stats * 16;
+       i += (long)gridDim.x * blockDim.x)
+    stats_partial[i] = 0.0;
+}
+
+static int g_fat_variant = -1;
+void fat_set_variant(int v) { g_fat_variant = v; }
+
+template <int MODE>
+static bool fat_bulk_launch(cudaStream_t st, const double* Q, const double* F, int m, const int32_t* labels, double* P,
+                            double* Z, int32_t* pred, double* stats_partial, int nblocks, long NT) {
+  if (m > 128 || m < 4) return false;
+  const size_t per_warp = (size_t)2 * NL * m * sizeof(double);   // NBUF buffers
+  int wpb = (int)((220 * 1024 - 512 - 16 * 12 * sizeof(double)) / per_warp);
+  if (wpb > 16) wpb = 16;
+  if (wpb < 4) return false;
+  const int grid = nblocks / 12;   // = number of SMs (fat_blocks): one persistent CTA per SM
+  if (grid < 1) return false;
+  const size_t sh = 512 + 16 * 12 * sizeof(double) + (size_t)wpb * per_warp;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(fat_bulk_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr = true;
+  }
+  fat_bulk_kernel<MODE><<<grid, 32 * wpb, sh, st>>>(Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
+  return true;
+}
+
 int fat_blocks(int num_sm) { return num_sm * 12; }
 
 template <int MODE>
@@ -937,6 +1141,23 @@ static void fat_launch(cudaStream_t st, const double* Q, const double* F, int m,
 
 void fat_kernel(cudaStream_t st, int mode, const double* Q, const double* F, int m, const int32_t* labels,
                 double* P, double* Z, int32_t* pred, double* stats_partial, int nblocks, long NT) {
+  // Measured on B200 (bench.py, m = 120): the register-resident kernel streams the label environment
+  // at 5.06 TB/s, the bulk-copy kernel at 4.77 TB/s with 2 buffers per warp (11 warps/SM) and
+  // 4.70 TB/s with 3 (7 warps/SM): shared memory caps the bytes in flight at about the level the
+  // 12 x 168-register warps reach anyway.  So the register kernel stays the default (variant 1);
+  // TNML_FAT=2 / tnml_set_option("fat_variant", 2) selects the bulk-copy kernel.
+  if (g_fat_variant < 0) {
+    const char* e = getenv("TNML_FAT");
+    g_fat_variant = e ? atoi(e) : 1;
+  }
+  if (g_fat_variant == 2 && NT >= 1024) {
+    bool done = false;
+    if (mode == FAT_GRAD) done = fat_bulk_launch<FAT_GRAD>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
+    else if (mode == FAT_PAP) done = fat_bulk_launch<FAT_PAP>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
+    else if (mode == FAT_COST) done = fat_bulk_launch<FAT_COST>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
+    else if (mode == FAT_BWD) done = fat_bulk_launch<FAT_BWD>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
+    if (done) return;
+  }
   switch (mode) {
     case FAT_GRAD:
       fat_launch<FAT_GRAD>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);

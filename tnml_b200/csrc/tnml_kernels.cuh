@@ -47,6 +47,9 @@ enum FatMode : int {
 void fat_kernel(cudaStream_t st, int mode, const double* Q, const double* F, int m, const int32_t* labels,
                 double* P, double* Z, int32_t* pred, double* stats_partial, int nblocks, long NT);
 int fat_blocks(int num_sm);
+// 1 (default): register-resident kernel; 2: bulk-async-copy (TMA, cp.async.bulk + mbarrier) double-buffered
+// kernel for m <= 128 from 1024 images on (measured slower: 4.77 vs 5.06 TB/s)
+void fat_set_variant(int v);
 void reduce_stats(cudaStream_t st, const double* stats_partial, int nblocks, double* stats /*[16]*/);
 
 // ---- small dense tensor helpers ---------------------------------------------
