@@ -13,7 +13,7 @@ cap() {  # name regex skip
       -o gpurun_out/prof_${TAG}_$1 $B > gpurun_out/ncu_$1.log 2>&1
 }
 cap krgemm2 krgemm2_kernel 231
-cap krgram krgram_kernel 5
+cap krgram2 krgram2_kernel 5
 cap fat fat_kernel_t 20
 cap jacobi_cluster jacobi_cluster_kernel 5
 cap qr_block qr_block_kernel 3
