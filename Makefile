@@ -29,3 +29,11 @@ clean:
 	rm -f $(LIB) $(HOSTBIN) tnml_b200/host/fulltest oracle/_build/fixedl_ref_cpu
 
 .PHONY: all lib host oracle clean
+
+# micro-benchmarks behind the design decisions (run on the GPU box)
+TOOLS := tools/dmma_bench tools/dmma_lds_bench tools/imma_bench tools/lat_bench tools/krgemm_bench_base
+tools: $(TOOLS)
+tools/krgemm_bench_base: tools/krgemm_bench.cu $(CSRC)
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o $@ $<
+tools/%: tools/%.cu
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o $@ $<
