@@ -13,7 +13,9 @@ $(LIB): $(CSRC) $(wildcard tnml_b200/csrc/*.cuh) include/tnml_b200.h
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC) -ldl
 
 # drop-in `fixedL <inputfile>` program (host C++ over the C-ABI)
-host: $(HOSTBIN) tnml_b200/host/fulltest
+host: $(HOSTBIN) tnml_b200/host/fulltest tnml_b200/host/hosttest
+tnml_b200/host/hosttest: tnml_b200/host/hosttest.cc tnml_b200/host/itensor_lite.h tnml_b200/host/initial_w.h
+	$(CXX) -O2 -std=c++17 -Wall -o $@ tnml_b200/host/hosttest.cc
 tnml_b200/host/fulltest: tnml_b200/host/fulltest.cc tnml_b200/host/itensor_lite.h tnml_b200/host/mnist.h include/tnml_b200.h $(LIB)
 	$(CXX) -O2 -std=c++17 -Wall -o $@ tnml_b200/host/fulltest.cc -Ltnml_b200 -ltnml_b200 -Wl,-rpath,'$$ORIGIN/..' -pthread
 $(HOSTBIN): tnml_b200/host/fixedL.cc tnml_b200/host/initial_w.h tnml_b200/host/itensor_lite.h tnml_b200/host/mnist.h include/tnml_b200.h $(LIB)
@@ -26,7 +28,7 @@ oracle/_build/fixedl_ref_cpu: oracle/fixedl_ref_cpu.cpp
 	$(CXX) -O3 -march=native -std=c++17 -pthread -o $@ $<
 
 clean:
-	rm -f $(LIB) $(HOSTBIN) tnml_b200/host/fulltest oracle/_build/fixedl_ref_cpu
+	rm -f $(LIB) $(HOSTBIN) tnml_b200/host/fulltest tnml_b200/host/hosttest oracle/_build/fixedl_ref_cpu
 
 .PHONY: all lib host oracle clean
 

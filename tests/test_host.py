@@ -77,6 +77,17 @@ def _host_bin():
     return p
 
 
+def test_host_selftest():
+    """itensor_lite.h (contraction, addition, commonIndex, Sweeps, Args, sweepnext) and initial_w.h
+    (small SVD, MPS direct sum + compression, overlap bilinearity, Maxm) -- C++ self-test, no GPU."""
+    _host_bin()
+    p = os.path.join(ROOT, "tnml_b200", "host", "hosttest")
+    if not os.path.exists(p):
+        subprocess.run(["make", "-s", "host"], cwd=ROOT, check=True)
+    r = subprocess.run([p], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "hosttest: PASS" in r.stdout, r.stdout + r.stderr
+
+
 def test_fixedL_usage_returns_zero():
     r = subprocess.run([_host_bin()], capture_output=True, text=True)
     assert r.returncode == 0 and "Usage:" in r.stdout and "inputfile" in r.stdout   # fixedL.cc:579-583

@@ -1661,10 +1661,12 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
         }
         const int cross_now = (g_svd_cross >= 0) ? g_svd_cross : cross_only;
         if (cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<8>, A, Jm, rows, ns, gld, nblk_e, tol2, conv, max_sweeps,
-                               cross_now, w.info, w.sweepmax, w.flags) != cudaSuccess)
-          return -2;
-        nl += 2;
-        return 1;   // convergence flag is in info[6]: the caller reads it with the truncation results (one sync)
+                               cross_now, w.info, w.sweepmax, w.flags) == cudaSuccess) {
+          nl += 2;
+          return 1;   // convergence flag is in info[6]: the caller reads it with the truncation results (one sync)
+        }
+        cudaGetLastError();   // cluster launch refused (e.g. no GPC with 16 free SMs): multi-launch path from now on
+        use_cluster = 0;
       }
     }
   }

@@ -362,4 +362,63 @@ RMPS initial_sum(int N, int d, int c, int NL, ImgVec const& train, Phi const& ph
   return W;
 }
 
+// any MPS (label-free, or with the label index on one site) -> RMPS; the label index is merged
+// into that site's physical index ((s, l), p = d*NL) so that contractions run over it too
+inline RMPS to_raw(itensor::MPS const& W) {
+  const int N = W.N();
+  RMPS R(N + 1);
+  for (int j = 1; j <= N; ++j) {
+    auto const& is = W.A(j).inds();
+    if (is.size() == 3) {
+      R[j].ml = is[0].m();
+      R[j].p = is[1].m();
+      R[j].mr = is[2].m();
+      R[j].a = W.A(j).data();
+    } else if (is.size() == 4) {   // (left, site, right, L), row-major
+      const long ml = is[0].m(), d = is[1].m(), mr = is[2].m(), nl = is[3].m();
+      R[j].ml = ml;
+      R[j].p = d * nl;
+      R[j].mr = mr;
+      R[j].a.resize(ml * d * nl * mr);
+      auto const& t = W.A(j).data();
+      for (long l = 0; l < ml; ++l)
+        for (long s = 0; s < d; ++s)
+          for (long r = 0; r < mr; ++r)
+            for (long q = 0; q < nl; ++q) R[j].a[(l * d * nl + s * nl + q) * mr + r] = t[((l * d + s) * mr + r) * nl + q];
+    } else {
+      itensor::Error("MPS site tensor of unexpected rank");
+    }
+  }
+  return R;
+}
+
 }  // namespace initw
+
+// ---- the ITensor-shaped entry points fixedL.cc uses on whole MPS (fixedL.cc:697,710,723,729) ----
+namespace itensor {
+
+// overlap(psi, phi) = <psi|phi>, every site (and label) index contracted
+inline Real overlap(MPS const& A, MPS const& B) { return initw::overlap(initw::to_raw(A), initw::to_raw(B)); }
+
+// sum(vector<MPS>, {"Cutoff", c, "Maxm", m}): label-free terms over the same site indices
+inline MPS sum(std::vector<MPS> const& terms, Args const& args = Args()) {
+  if (terms.empty()) Error("sum of zero MPS");
+  std::vector<initw::RMPS> raw;
+  for (auto const& t : terms) raw.push_back(initw::from_mps(t));
+  const Real cutoff = args.getReal("Cutoff", 1E-13);
+  const long maxm = args.getInt("Maxm", 1000000);
+  const bool dorel = args.getBool("DoRelCutoff", false);
+  initw::RMPS R = initw::sum(raw, cutoff, maxm, dorel);
+  const int N = terms[0].N();
+  MPS W(N);
+  std::vector<Index> links(N + 1);
+  links[0] = Index("l0", 1, Link);
+  for (int j = 1; j <= N; ++j) links[j] = Index(format("l%d", j), R[j].mr, Link);
+  for (int j = 1; j <= N; ++j) {
+    Index site = terms[0].A(j).inds().at(1);
+    W.setA(j, ITensor(std::vector<Index>{links[j - 1], site, links[j]}, std::vector<Real>(R[j].a)));
+  }
+  return W;
+}
+
+}  // namespace itensor
