@@ -507,6 +507,39 @@ def test_svd_qr_preconditioned_path(capi, b, ha):
     h.close()
 
 
+@pytest.mark.parametrize("b,ha", [(7, 1), (8, 2), (7, 2)])
+def test_svd_tall_class_c(capi, b, ha):
+    """Class-C bond matrices at larger link dimension (1280-1400 x 128-140): the first QR and the
+    apply-Q of the tall side run from shared-memory-resident columns (> 1280 rows)."""
+    feat, labels, W = make_problem(N=16, NT=32, m0=70)
+    ts = O.TrainStates(feat, labels)
+    ts.init(W)
+    h = _gpu_state(capi, feat, labels, W)
+    _walk_both(h, ts, W, capi, b)
+    rng = np.random.default_rng(b * 10 + ha)
+    B0 = O.form_bond(W[b], W[b + 1])
+    B = B0 + 1e-3 * np.linalg.norm(B0) / np.sqrt(B0.size) * rng.standard_normal(B0.shape)
+    assert max(B.shape[0], B.shape[3]) * 2 * 10 > 1280
+    for (maxm, minm, cutoff) in [(70, 35, 1e-10), (1000, 1, 0.0)]:
+        Wb, Wb1, m, te = O.svd_split(B, b, ha, 8, maxm, minm, cutoff)
+        h.bond_load(B)
+        gm, gte = h.svd_split(capi.FROMLEFT if ha == 1 else capi.FROMRIGHT, cutoff, maxm, minm)
+        assert gm == m
+        assert abs(gte - te) <= 1e-8 * max(te, 1e-300) + 1e-22 * np.linalg.norm(B) ** 2
+        gWb, gWb1 = h.get_site(b), h.get_site(b + 1)
+        assert rel(O.form_bond(gWb, gWb1), O.form_bond(Wb, Wb1)) < 1e-10
+        iso = gWb if ha == 1 else gWb1
+        if ha == 1:
+            U = (np.transpose(iso, (0, 1, 3, 2)) if iso.ndim == 4 else iso).reshape(-1, m)
+            assert rel(U.T @ U, np.eye(m)) < 1e-11
+        else:
+            V = iso.reshape(m, -1)
+            assert rel(V @ V.T, np.eye(m)) < 1e-11
+        h.set_site(b, W[b])
+        h.set_site(b + 1, W[b + 1])
+    h.close()
+
+
 @pytest.mark.parametrize("b", [3, 4, 7])
 def test_cg_reuse_forward_option(capi, b):
     """cg_reuse_forward=1 (linear update of the forward outputs) is the same mathematics as the

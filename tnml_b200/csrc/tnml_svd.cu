@@ -1083,7 +1083,7 @@ __global__ void svd_scatter_kernel(const double* __restrict__ X, const double* _
 // memory), then forms its own reflector.  No grid-wide barrier.  All ns warps
 // must be co-resident (ns/8 CTAs <= number of SMs).
 template <int RPL>   // rows per lane: nb <= 32*RPL
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 1)
 qr_dataflow_kernel(double* __restrict__ X, int nb, int ns, double* __restrict__ tau, volatile int* ready) {
   const int lane = threadIdx.x & 31;
   const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -1163,6 +1163,93 @@ qr_dataflow_kernel(double* __restrict__ X, int nb, int ns, double* __restrict__ 
   __threadfence();
   __syncwarp();
   if (lane == 0) ready[j] = 1;
+}
+
+// Tall columns (class-C bond matrices, nb = 20 m > 1280 rows): 75+ rows per lane do not fit the
+// register file (the register-resident kernels above spilled 1-8 KB per thread and made the first
+// QR of a 2400 x 240 matrix cost 9 ms), so the warp's column lives in shared memory and every
+// loop is a plain strided loop.  Same dataflow: one warp per column, reflector k consumed as soon
+// as its flag is published.
+__global__ void __launch_bounds__(256, 1)
+qr_dataflow_smem_kernel(double* __restrict__ X, int nb, int ns, double* __restrict__ tau, volatile int* ready) {
+  extern __shared__ __align__(16) double qcol[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * 8 + warp;
+  if (j >= ns) return;
+  double* a = qcol + (long)warp * nb;
+  double* aj = X + (long)j * nb;
+  for (int r = lane; r < nb; r += 32) a[r] = aj[r];
+  __syncwarp();
+  for (int k = 0; k < j; ++k) {
+    if (lane == 0)
+      while (ready[k] == 0) {
+      }
+    __syncwarp();
+    __threadfence();
+    const double* vk = X + (long)k * nb;
+    const double tk = __ldcg(tau + k);
+    double dot = (lane == 0) ? a[k] : 0.0;               // v(k) = 1
+    for (int r = k + 1 + lane; r < nb; r += 32) dot = fma(__ldcg(vk + r), a[r], dot);
+    dot = wsum(dot);
+    const double f = tk * dot;
+    if (lane == 0) a[k] -= f;
+    for (int r = k + 1 + lane; r < nb; r += 32) a[r] = fma(-f, __ldcg(vk + r), a[r]);
+    __syncwarp();
+  }
+  // own reflector (LAPACK dlarfg): H = I - tau v v^T, v(j) = 1
+  const double alpha = a[j];
+  double xn2 = 0.0;
+  for (int r = j + 1 + lane; r < nb; r += 32) xn2 = fma(a[r], a[r], xn2);
+  xn2 = wsum(xn2);
+  double tj = 0.0, beta = alpha, scale = 0.0;
+  if (xn2 > 0.0) {
+    beta = -copysign(sqrt(fma(alpha, alpha, xn2)), alpha);
+    tj = (beta - alpha) / beta;
+    scale = 1.0 / (alpha - beta);
+  }
+  for (int r = lane; r < nb; r += 32) {
+    double out = a[r];
+    if (r == j) out = beta;
+    if (r > j) out = a[r] * scale;
+    __stcg(aj + r, out);
+  }
+  if (lane == 0) __stcg(tau + j, tj);
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) ready[j] = 1;
+}
+
+// Y[i] = Q * [src[:, perm[i]] * sc; 0] for tall columns: the vector lives in shared memory.
+__global__ void __launch_bounds__(256, 1)
+apply_q_smem_kernel(const double* __restrict__ X, const double* __restrict__ tau, const double* __restrict__ Jm,
+                    const int* __restrict__ perm, int nb, int ns, int m, double* __restrict__ Y,
+                    const double* __restrict__ scale_sig2, const int* __restrict__ rowperm) {
+  extern __shared__ __align__(16) double qcol[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i0 = blockIdx.x * 8 + warp;
+  if (i0 >= m) return;
+  double* y = qcol + (long)warp * nb;
+  const double* jc = Jm + (long)perm[i0] * ns;
+  double sc = 1.0;
+  if (scale_sig2 != nullptr) {
+    const double sg = sqrt(scale_sig2[perm[i0]]);
+    sc = (sg > 0.0) ? 1.0 / sg : 0.0;
+  }
+  for (int r = lane; r < nb; r += 32) y[r] = (r < ns) ? jc[r] * sc : 0.0;
+  __syncwarp();
+  for (int k = ns - 1; k >= 0; --k) {
+    const double* vk = X + (long)k * nb;
+    const double tk = tau[k];
+    double dot = (lane == 0) ? y[k] : 0.0;
+    for (int r = k + 1 + lane; r < nb; r += 32) dot = fma(__ldg(vk + r), y[r], dot);
+    dot = wsum(dot);
+    const double f = tk * dot;
+    if (lane == 0) y[k] -= f;
+    for (int r = k + 1 + lane; r < nb; r += 32) y[r] = fma(-f, __ldg(vk + r), y[r]);
+    __syncwarp();
+  }
+  double* out = Y + (long)i0 * nb;
+  for (int r = lane; r < nb; r += 32) out[rowperm ? rowperm[r] : r] = y[r];
 }
 
 // Same factorisation, 32 consecutive columns per CTA (32 warps): reflectors of the CTA's own
@@ -1349,7 +1436,7 @@ __global__ void rt_form_kernel(const double* __restrict__ X, int nb, int ns, dou
 // scale_sig2 != nullptr: the source column is sigma * unit vector, normalise it (zero if sigma = 0);
 // rowperm != nullptr: out[rowperm[r]] = y[r] (undo the column sort of the first QR).
 template <int RPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 1)
 apply_q_kernel(const double* __restrict__ X, const double* __restrict__ tau, const double* __restrict__ Jm,
                const int* __restrict__ perm, int nb, int ns, int m, double* __restrict__ Y,
                const double* __restrict__ scale_sig2, const int* __restrict__ rowperm) {
@@ -1823,7 +1910,14 @@ static int run_qr(cudaStream_t st, SvdWork& w, double* Xq, double* tau, int nb, 
   if (nb <= 32 * 8) launch_qr_block8(st, w, Xq, tau, nb, ns);
   else if (nb <= 32 * 20) launch_qr<20>(st, w, Xq, tau, nb, ns);
   else if (nb <= 32 * 40) launch_qr<40>(st, w, Xq, tau, nb, ns);
-  else launch_qr<96>(st, w, Xq, tau, nb, ns);
+  else {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(qr_dataflow_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr = true;
+    }
+    qr_dataflow_smem_kernel<<<(ns + 7) / 8, 256, (size_t)8 * nb * sizeof(double), st>>>(Xq, nb, ns, tau, w.ready);
+  }
   return 0;
 }
 static void run_apply_q(cudaStream_t st, const double* Xq, const double* tau, const double* src, const int* perm,
@@ -1831,7 +1925,15 @@ static void run_apply_q(cudaStream_t st, const double* Xq, const double* tau, co
   if (nb <= 32 * 8) launch_apply_q<8>(st, Xq, tau, src, perm, nb, ns, m, Yout, scale_sig2, rowperm);
   else if (nb <= 32 * 20) launch_apply_q<20>(st, Xq, tau, src, perm, nb, ns, m, Yout, scale_sig2, rowperm);
   else if (nb <= 32 * 40) launch_apply_q<40>(st, Xq, tau, src, perm, nb, ns, m, Yout, scale_sig2, rowperm);
-  else launch_apply_q<96>(st, Xq, tau, src, perm, nb, ns, m, Yout, scale_sig2, rowperm);
+  else {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(apply_q_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr = true;
+    }
+    apply_q_smem_kernel<<<(m + 7) / 8, 256, (size_t)8 * nb * sizeof(double), st>>>(Xq, tau, src, perm, nb, ns, m, Yout,
+                                                                               scale_sig2, rowperm);
+  }
 }
 
 int svd_split(cudaStream_t st, SvdWork& w, const double* Bc, BondGeom g, int dir, double cutoff, int maxm,
