@@ -5,6 +5,7 @@
   config 2  synthetic 14x14, NT=10000, maxm=50, 2 sweeps: sweep-average bond-updates/s
   config 3  synthetic 14x14, NT=60000, maxm=120, 2 sweeps: sweep-average + saturated-bond rate
   m=300     one class-L bond update at ml=mr=300 against the oracle (config 5 shape, small NT)
+  config 5  per-bond times at m=300 with one GPU's shard of images (131072) on a window of bonds
 
   python tools/run_configs.py [1] [2] [3] [300]      -> profiles/configs_r01.txt
 """
@@ -131,6 +132,43 @@ def m300():
     h.close()
 
 
+def config5(NT=131072, m=300):
+    """BASELINE config 5 shape (synthetic, m = 300) on a window of bonds: a class-L, the two class-C and
+    a class-R bond at m_l = m_r = 300 with the images of one GPU's shard (1e6 / 8 = 125k)."""
+    N = 24
+    pix, labels = data.synthetic_digits(NT, 14, seed=20260925)
+    feat = data.phi(pix[:, 86:86 + N])
+    W = data.random_mps(N, 2, m, seed=5)
+    h = capi.Handle(0)
+    h.set_images(feat, labels)
+    h.set_mps(W)
+    h.set_option("reserve_m", m)
+    h.init_envs()
+    for bb in range(1, 10):
+        h.set_bond(bb)
+        h.shift_env(bb, capi.FROMLEFT)
+    p = capi.BondParams(4, 0.0, 1e-10, 1e-10, m, m, 0)
+    say(f"== config 5 window: synthetic N={N} sites, NT={NT} images on one GPU, maxm=minm={m}, Npass=4 (jc={N // 2})")
+    for b in (10, 13, 14):
+        if b == 13:      # pass the two class-C bonds without optimising them (measured separately below)
+            for bb in (11, 12):
+                h.set_bond(bb)
+                h.shift_env(bb, capi.FROMLEFT)
+        h.set_timing(True)
+        h.stats(reset=True)
+        t0 = time.perf_counter()
+        r = h.bond_update(b, 1, p)
+        h.synchronize()
+        dt = time.perf_counter() - t0
+        st = h.stats(reset=True)
+        h.set_timing(False)
+        cls = "L" if b <= N // 2 - 2 else ("C" if b <= N // 2 else "R")
+        say(f"   bond {b} class {cls} m {r.origm}->{r.newm}: {dt * 1e3:.1f} ms = {1 / dt:.2f} bond-updates/s "
+            f"({NT / dt / 1e6:.2f} M images*bonds/s); phases ms: proj {st.ms_proj:.1f} grad {st.ms_grad:.1f} fat {st.ms_fat:.1f} "
+            f"svd {st.ms_svd:.1f} ({r.svd_sweeps} sweeps) shift {st.ms_shift:.1f}; cost/NT {r.cost / NT:.6f}")
+    h.close()
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["1", "2", "3", "300"]
     say(f"# run_configs {' '.join(which)}  ({capi.load_library().tnml_version().decode()})")
@@ -142,3 +180,5 @@ if __name__ == "__main__":
         sweeps(10000, 50, 2, "config 2 (2 of 10 sweeps)")
     if "3" in which:
         sweeps(60000, 120, 2, "config 3 (2 of 20 sweeps)")
+    if "5" in which:
+        config5()
