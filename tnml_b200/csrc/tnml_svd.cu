@@ -402,21 +402,21 @@ jacobi_gram_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows, in
   //      column parity): 16 independent 16-byte loads in flight per thread, no index division.
   const int rc2 = tid & 255, cpar = tid >> 8;
   const int ld2 = ld >> 1, rows2 = rows >> 1, tot2 = tot >> 1;   // rows, ns are even (2m or 2m*NL)
-  if (rc2 < ld2) {
+  for (int rr2 = rc2; rr2 < ld2; rr2 += 256) {   // more than 512 staged rows (m > 128): several passes
     double2 v[NC / CP];
 #pragma unroll
     for (int it = 0; it < NC / CP; ++it) {
       const int k = cpar + CP * it;
       const int c = (k < W) ? (c0 + k) : (c1 + k - W);
       v[it] = make_double2(0.0, 0.0);
-      if (c < ns && rc2 < tot2)
-        v[it] = (rc2 < rows2) ? __ldcg(reinterpret_cast<const double2*>(A + (long)c * rows) + rc2)
-                              : __ldcg(reinterpret_cast<const double2*>(Jm + (long)c * ns) + (rc2 - rows2));
+      if (c < ns && rr2 < tot2)
+        v[it] = (rr2 < rows2) ? __ldcg(reinterpret_cast<const double2*>(A + (long)c * rows) + rr2)
+                              : __ldcg(reinterpret_cast<const double2*>(Jm + (long)c * ns) + (rr2 - rows2));
     }
 #pragma unroll
     for (int it = 0; it < NC / CP; ++it) {
       const int k = cpar + CP * it;
-      reinterpret_cast<double2*>(S + (long)k * ld)[rc2] = v[it];
+      reinterpret_cast<double2*>(S + (long)k * ld)[rr2] = v[it];
     }
   }
   for (int i = tid; i < NC * GLD; i += NTH) RA[i] = ((i / GLD) == (i % GLD)) ? 1.0 : 0.0;
@@ -580,17 +580,17 @@ jacobi_gram_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows, in
   __syncthreads();
   tstamp[4] = clock64();
   // ---- write back
-  if (rc2 < tot2) {
+  for (int rr2 = rc2; rr2 < tot2; rr2 += 256) {
 #pragma unroll
     for (int it = 0; it < NC / CP; ++it) {
       const int k = cpar + CP * it;
       const int c = (k < W) ? (c0 + k) : (c1 + k - W);
       if (c < ns) {
-        const double2 v = reinterpret_cast<const double2*>(S + (long)k * ld)[rc2];
-        if (rc2 < rows2)
-          __stcg(reinterpret_cast<double2*>(A + (long)c * rows) + rc2, v);
+        const double2 v = reinterpret_cast<const double2*>(S + (long)k * ld)[rr2];
+        if (rr2 < rows2)
+          __stcg(reinterpret_cast<double2*>(A + (long)c * rows) + rr2, v);
         else
-          __stcg(reinterpret_cast<double2*>(Jm + (long)c * ns) + (rc2 - rows2), v);
+          __stcg(reinterpret_cast<double2*>(Jm + (long)c * ns) + (rr2 - rows2), v);
       }
     }
   }
@@ -1683,7 +1683,7 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
   const int GW = gram_w;
   const size_t need_gram = ((size_t)2 * GW * gld + 3 * 2 * GW * GLD + 4 * GW) * sizeof(double) +
                            (size_t)(2 * GW - 1) * GW * sizeof(unsigned short) + (size_t)(2 * GW - 1) * 2 * GW + 16;
-  const bool gram = use_gram && need_gram <= 220 * 1024 && ns > GW && gld <= 512 && (rows % 2 == 0) && (ns % 2 == 0);
+  const bool gram = use_gram && need_gram <= 220 * 1024 && ns > GW && (rows % 2 == 0) && (ns % 2 == 0);
   const int bw = gram ? GW : (Wd ? Wd : JW);
   const int nblk = (ns + bw - 1) / bw;
   const int nblk_e = (nblk % 2) ? nblk + 1 : nblk;
