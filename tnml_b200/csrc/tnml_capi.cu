@@ -776,6 +776,12 @@ int tnml_destroy(tnml_handle h) {
     if (p) cudaFree(p);
   for (auto& ge : h->svd.gexec)
     if (ge) cudaGraphExecDestroy(ge);
+  if (h->svd.st2) {
+    cudaStreamSynchronize(h->svd.st2);
+    cudaStreamDestroy(h->svd.st2);
+    cudaEventDestroy(h->svd.ev_fork);
+    cudaEventDestroy(h->svd.ev_join);
+  }
   if (h->hpin) cudaFreeHost(h->hpin);
   for (auto& e : h->evs) {
     cudaEventDestroy(e.a);

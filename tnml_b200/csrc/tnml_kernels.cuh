@@ -105,6 +105,8 @@ struct SvdWork {
   long capM2 = 0;
   int use_qr = -1;         // -1 auto, 0 never, 1 one QR, 3 sort + two QRs (TNML_SVD_QR)
   int hint_m = 0;          // largest link dimension expected (maxm): buffers are sized for it at once
+  cudaStream_t st2 = nullptr;              // side stream: the two apply-Q launches run concurrently
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // one Jacobi sweep captured as a CUDA graph, one executable per (buffers, dims) seen -- in a real
   // sweep the bond matrix has a different size at almost every bond, and re-instantiating the
   // graph every time costs more than it saves

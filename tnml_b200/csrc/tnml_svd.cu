@@ -2010,8 +2010,26 @@ int svd_split(cudaStream_t st, SvdWork& w, const double* Bc, BondGeom g, int dir
   if (qr2) {
     // X P0 = Q1 W Sigma (Q2 J)^T with W Sigma = the rotated columns of R2^T:
     // big side = Q1 [W; 0], small side = P0 (Q2 J)
-    run_apply_q(st, w.X, w.tau, w.M2, w.perm, nb, ns, m, w.Y, w.sig2, nullptr);
-    run_apply_q(st, w.M, w.tau2, w.J, w.perm, ns, ns, m, w.Y2, nullptr, w.perm0);
+    // the two applications are independent (15 CTAs each at m = 120): run them side by side
+    if (!w.st2) {
+      if (cudaStreamCreateWithFlags(&w.st2, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&w.ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        w.st2 = nullptr;
+      }
+    }
+    if (w.st2) {
+      cudaEventRecord(w.ev_fork, st);
+      cudaStreamWaitEvent(w.st2, w.ev_fork, 0);
+      run_apply_q(w.st2, w.M, w.tau2, w.J, w.perm, ns, ns, m, w.Y2, nullptr, w.perm0);
+      cudaEventRecord(w.ev_join, w.st2);
+      run_apply_q(st, w.X, w.tau, w.M2, w.perm, nb, ns, m, w.Y, w.sig2, nullptr);
+      cudaStreamWaitEvent(st, w.ev_join, 0);
+    } else {
+      run_apply_q(st, w.X, w.tau, w.M2, w.perm, nb, ns, m, w.Y, w.sig2, nullptr);
+      run_apply_q(st, w.M, w.tau2, w.J, w.perm, ns, ns, m, w.Y2, nullptr, w.perm0);
+    }
     svd_scatter_qr2_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(w.Y, w.Y2, w.sig2, w.perm, sg, isoIsA, m,
                                                                         Wb_out, Wb1_out);
     nl += 3;
