@@ -195,3 +195,38 @@ def test_cpp_literal_port_matches_numpy_oracle(tmp_path, b, nthread):
     # final cost: the numpy oracle run with 1/2/5 ParallelDo shards already spreads by
     # 4e-5 at the class-C bond (b=4); elsewhere summation order matters < 1e-9
     assert abs(out["C"] - Co) < (1e-3 if b == 4 else 1e-7) * Co and abs(out["ncor"] - ncor) <= 2
+
+
+def _mps_dense(R):
+    """Contract a raw MPS (list of [ml, p, mr], 1-indexed) to the dense tensor [p1, p2, ..., pN]."""
+    T = R[1][0]                                   # [p, mr]
+    for j in range(2, len(R)):
+        T = np.tensordot(T, R[j], axes=([-1], [0]))
+    return T[..., 0]
+
+
+def test_mps_sum_is_exact_without_truncation():
+    """Oracle of the initial-W construction (fixedL.cc:702-728): direct sum + orthogonalize with
+    Cutoff 0 reproduces the dense sum of the terms; with Maxm the result is the best approximation
+    bond by bond (error bounded by the discarded weight) and never exceeds Maxm."""
+    rng = np.random.default_rng(4)
+    N = 6
+
+    def rand_mps(m):
+        dims = [1] + [m] * (N - 1) + [1]
+        return [None] + [rng.standard_normal((dims[j - 1], 2, dims[j])) for j in range(1, N + 1)]
+    terms = [rand_mps(2), rand_mps(3), rand_mps(1)]
+    dense = sum(_mps_dense(t) for t in terms)
+    S = O.mps_sum([[None] + [a.copy() for a in t[1:]] for t in terms], 0.0, 10 ** 6)
+    assert np.allclose(_mps_dense(S), dense, rtol=0, atol=1e-12 * np.abs(dense).max())
+    assert abs(O.mps_overlap(S, S) - np.sum(dense * dense)) < 1e-10 * np.sum(dense * dense)
+    T = O.mps_sum([[None] + [a.copy() for a in t[1:]] for t in terms], 0.0, 3)
+    assert max(a.shape[2] for a in T[1:]) <= 3
+    err = np.linalg.norm(_mps_dense(T) - dense) / np.linalg.norm(dense)
+    assert 0 < err < 0.9                               # truncated, but still an approximation of the sum
+    # product states: the sum of identical states is 2 x the state with bond dimension 1
+    f = rng.uniform(0, 1, (N, 2))
+    p = O.mps_product_state(f)
+    P2 = O.mps_sum([p, O.mps_product_state(f)], 1e-10, 10)
+    assert max(a.shape[2] for a in P2[1:]) == 1
+    assert np.allclose(_mps_dense(P2), 2 * _mps_dense(p), atol=1e-12)
