@@ -230,3 +230,23 @@ def test_mps_sum_is_exact_without_truncation():
     P2 = O.mps_sum([p, O.mps_product_state(f)], 1e-10, 10)
     assert max(a.shape[2] for a in P2[1:]) == 1
     assert np.allclose(_mps_dense(P2), 2 * _mps_dense(p), atol=1e-12)
+
+
+def test_ozaki_slicing_is_error_free_up_to_the_truncation():
+    """oracle/ozaki.py (checker for the planned int8 tensor-core route): slices reconstruct the operand
+    to 2^-7s, every slice fits a signed 7-bit integer, the product error falls by 2^-7 per slice and
+    reaches float64 level at 8 slices."""
+    from oracle import ozaki
+    rng = np.random.default_rng(1)
+    A = rng.standard_normal((64, 48)) * np.exp(3 * rng.standard_normal((64, 1)))
+    B = rng.standard_normal((48, 40)) * np.exp(3 * rng.standard_normal((1, 40)))
+    q, sc = ozaki.slices(A, 1, 6)
+    assert all(np.abs(x).max() <= 127 for x in q)
+    rec = sum(x * 2.0 ** (-7 * (i + 1)) for i, x in enumerate(q)) * sc
+    # 6 slices = 42 bits below the power-of-two scale, which is at most 4x the row maximum
+    assert np.max(np.abs(rec - A) / np.max(np.abs(A), axis=1, keepdims=True)) < 2.0 ** (-39)
+    ref = A @ B
+    bound = np.abs(A) @ np.abs(B)
+    errs = [np.max(np.abs(ozaki.ozaki_matmul(A, B, s) - ref) / bound) for s in (4, 6, 8)]
+    assert errs[0] < 1e-6 and errs[1] < 1e-10 and errs[2] < 1e-14
+    assert errs[0] > 100 * errs[1] and errs[1] > 100 * errs[2]    # about 2^-14 per two slices

@@ -29,33 +29,11 @@ N = 196
 NSLICE = None      # None = plain float64
 
 
-def slices(M, axis, s):
-    """Scale along `axis` (1: per row, 0: per column) to |x| < 1 and cut into s signed 7-bit slices."""
-    mx = np.max(np.abs(M), axis=axis, keepdims=True)
-    e = np.where(mx > 0, np.ceil(np.log2(np.where(mx > 0, mx, 1.0))) + 1, 0.0)
-    r = M / np.exp2(e)
-    out = []
-    for _ in range(s):
-        r = r * 128.0
-        q = np.trunc(r)
-        out.append(q.astype(np.int64))
-        r = r - q
-    return out, np.exp2(e)
+from oracle.ozaki import ozaki_matmul as _ozaki  # noqa: E402
 
 
 def ozaki_matmul(A, B, s):
-    """A @ B with both operands cut into s slices; products of slice pairs with i + j < s."""
-    if s is None:
-        return A @ B
-    As, ea = slices(A, 1, s)
-    Bs, eb = slices(B, 0, s)
-    C = np.zeros((A.shape[0], B.shape[1]))
-    for lev in range(s - 1, -1, -1):            # smallest terms first
-        acc = np.zeros((A.shape[0], B.shape[1]), dtype=np.int64)
-        for i in range(lev + 1):
-            acc += As[i] @ Bs[lev - i]          # exact (int64 here, int32 per 133k-row chunk on the device)
-        C += acc.astype(np.float64) * 2.0 ** (-7 * (lev + 2))
-    return C * ea * eb
+    return A @ B if s is None else _ozaki(A, B, s)
 
 
 proj0, back0 = O.project, O.backproject
