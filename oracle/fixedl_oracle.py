@@ -306,12 +306,22 @@ def project(B, ts: TrainStates, sl=slice(None), literal=False):
         return np.einsum("astb,nastbl->nl", B, v)
     l, x, y, r = _lr(ts, sl)
     if B.ndim == 5:                       # class C: label on the bond tensor
-        T = np.einsum("na,ns,astbl->ntbl", l, x, B)
-        return np.einsum("ntbl,nt,nb->nl", T, y, r)
+        n, ml = l.shape
+        d, mr = B.shape[2], B.shape[3]
+        LX = (l[:, :, None] * x[:, None, :]).reshape(n, -1)                 # [n, (a s)]
+        T = (LX @ B.reshape(LX.shape[1], -1)).reshape(n, d, mr, NL)          # BLAS: [n, t, b, l]
+        YR = y[:, :, None] * r[:, None, :]                                   # [n, t, b]
+        return np.einsum("ntbl,ntb->nl", T, YR)
+    n = x.shape[0]
+    ml, d, _, mr = B.shape
     if r.ndim == 3:                       # class L: fat right env
-        Q = np.einsum("na,ns,astb,nt->nb", l, x, B, y, optimize=True)
+        LX = (l[:, :, None] * x[:, None, :]).reshape(n, -1)                 # [n, (a s)]
+        T = (LX @ B.reshape(ml * d, d * mr)).reshape(n, d, mr)               # BLAS: [n, t, b]
+        Q = np.einsum("ntb,nt->nb", T, y)
         return np.einsum("nb,nlb->nl", Q, r)
-    Q = np.einsum("nb,nt,astb,ns->na", r, y, B, x, optimize=True)   # class R
+    YR = (y[:, :, None] * r[:, None, :]).reshape(n, -1)                     # class R: [n, (t b)]
+    T = (YR @ B.reshape(ml * d, d * mr).T).reshape(n, ml, d)                 # BLAS: [n, a, s]
+    Q = np.einsum("nas,ns->na", T, x)
     return np.einsum("na,nla->nl", Q, l)
 
 
@@ -324,12 +334,20 @@ def backproject(dP, Bshape, ts: TrainStates, sl=slice(None), literal=False):
         return np.einsum("nl,nastbl->astb", dP, v)
     l, x, y, r = _lr(ts, sl)
     if len(Bshape) == 5:
-        return np.einsum("nl,na,ns,nt,nb->astbl", dP, l, x, y, r, optimize=True)
+        n = l.shape[0]
+        LX = (l[:, :, None] * x[:, None, :]).reshape(n, -1)                 # [n, (a s)]
+        YRP = ((y[:, :, None] * r[:, None, :])[:, :, :, None] * dP[:, None, None, :]).reshape(n, -1)
+        return (LX.T @ YRP).reshape(Bshape)                                  # BLAS: [(a s), (t b l)]
+    n = x.shape[0]
     if r.ndim == 3:
         Z = np.einsum("nl,nlb->nb", dP, r)
-        return np.einsum("na,ns,nt,nb->astb", l, x, y, Z, optimize=True)
+        LX = (l[:, :, None] * x[:, None, :]).reshape(n, -1)                 # [n, (a s)]
+        YZ = (y[:, :, None] * Z[:, None, :]).reshape(n, -1)                 # [n, (t b)]
+        return (LX.T @ YZ).reshape(Bshape)                                   # BLAS
     Z = np.einsum("nl,nla->na", dP, l)
-    return np.einsum("na,ns,nt,nb->astb", Z, x, y, r, optimize=True)
+    ZX = (Z[:, :, None] * x[:, None, :]).reshape(n, -1)
+    YR = (y[:, :, None] * r[:, None, :]).reshape(n, -1)
+    return (ZX.T @ YR).reshape(Bshape)
 
 
 def argmax_first(w: np.ndarray) -> np.ndarray:

@@ -250,3 +250,30 @@ def test_ozaki_slicing_is_error_free_up_to_the_truncation():
     errs = [np.max(np.abs(ozaki.ozaki_matmul(A, B, s) - ref) / bound) for s in (4, 6, 8)]
     assert errs[0] < 1e-6 and errs[1] < 1e-10 and errs[2] < 1e-14
     assert errs[0] > 100 * errs[1] and errs[1] > 100 * errs[2]    # about 2^-14 per two slices
+
+
+def test_sharded_oracle_equals_whole():
+    """tests/helpers.ShardedOracle (the checker of the large-shape GPU tests) == the plain oracle."""
+    from tests.helpers import ShardedOracle, make_problem, rel
+    feat, labels, W = make_problem(N=10, NT=300, m0=4)
+    ts = O.TrainStates(feat, labels)
+    ts.init(W)
+    so = ShardedOracle(feat, labels, chunk=128)
+    so.init(W)
+    for b in range(1, 7):
+        ts.set_bond(b)
+        so.set_bond(b)
+        B = O.form_bond(W[b], W[b + 1])
+        assert rel(so.project(B), O.project(B, ts)) < 1e-13
+        C, CL, nc = O.quadcost(B, ts, detail=True)
+        c, cl, n = so.quadcost(B)
+        assert abs(c - C) < 1e-12 * C and n == nc and rel(cl, CL) < 1e-12
+        Bo, costs, rn = O.cgrad(B, ts, 3, 1e-4)
+        Bs, cs, rs, steps = so.cgrad(B, 3, 1e-4)
+        B1, _, _ = O.cgrad(B, ts, 1, 1e-4)
+        # sharp on one-step quantities only: the CG amplifies the shard-order rounding (DESIGN.md 3)
+        assert rel(cs[:1], costs[:1]) < 1e-12 and rel(steps[0], B1 - B) < 1e-10 and len(steps) == 3
+        assert rel(Bs, Bo) < 1e-2
+        ts.shiftE(W, b, "Fromleft")
+        so.shiftE(W, b, "Fromleft")
+        assert rel(so.slot(b), ts.slot[b]) < 1e-13

@@ -128,6 +128,7 @@ struct tnml_handle_s {
   int moving = 1;                // 1: sweeping right (Fromleft), 2: sweeping left
   int32_t* pred = nullptr;
   double* stats_partial = nullptr;
+  unsigned* ticket = nullptr;   // last-CTA ticket of the statistics reduction inside fat_kernel
   int nfat_blocks = 0;
   double* dscal = nullptr;  // [32] device scalars
   double* dot_scratch = nullptr;
@@ -446,12 +447,10 @@ int forward(tnml_handle h, const double* X, int mode, double* dstats, double* Po
     {
       PhaseTimer t(h, PH_FAT);
       fat_kernel(h->st, mode, h->Q.p, fat.p, mf, h->labels, Pout, h->Z.p, h->pred, h->stats_partial,
-                 h->nfat_blocks, NT);
-      CKL();
-      reduce_stats(h->st, h->stats_partial, h->nfat_blocks, dstats);
+                 h->nfat_blocks, NT, dstats, h->ticket);
       CKL();
     }
-    h->stats.launches += 3;
+    h->stats.launches += 2;
     h->stats.alg_flops += (double)NT * (8.0 * mt * mf + 2.0 * NL * mf * (mode == FAT_GRAD ? 2 : 1));
     h->stats.alg_bytes += 8.0 * NT * ((double)mt + (double)NL * mf + 4);
   } else {
@@ -467,12 +466,10 @@ int forward(tnml_handle h, const double* X, int mode, double* dstats, double* Po
     {
       PhaseTimer t(h, PH_FAT);
       fat_kernel(h->st, mode == FAT_GRAD ? FAT_GRAD_OUTER : mode, re.p, h->Q.p, g.mr, h->labels, Pout, h->Z.p,
-                 h->pred, h->stats_partial, h->nfat_blocks, NT);
-      CKL();
-      reduce_stats(h->st, h->stats_partial, h->nfat_blocks, dstats);
+                 h->pred, h->stats_partial, h->nfat_blocks, NT, dstats, h->ticket);
       CKL();
     }
-    h->stats.launches += 3;
+    h->stats.launches += 2;
     h->stats.alg_flops += (double)NT * (8.0 * NL * g.ml * g.mr + 2.0 * NL * g.mr);
     h->stats.alg_bytes += 8.0 * NT * ((double)g.ml + g.mr + 4);
   }
@@ -577,18 +574,16 @@ int grad_from_P(tnml_handle h, const double* X, double lambda, double* hstats) {
       const EnvRef& fat = (h->cls == 0) ? re : le;
       TRY(ensure(h, h->Z, (size_t)NT * fat.m, (size_t)NT * std::max(fat.m, h->reserve_m)));
       fat_kernel(h->st, FAT_BWD, h->Q.p, fat.p, fat.m, h->labels, h->P, h->Z.p, h->pred, h->stats_partial,
-                 h->nfat_blocks, NT);
+                 h->nfat_blocks, NT, h->dscal, h->ticket);
       h->stats.alg_bytes += 8.0 * NT * ((double)NL * fat.m + fat.m + NL);
       h->stats.alg_flops += (double)NT * 2.0 * NL * fat.m;
     } else {
       TRY(ensure(h, h->Z, (size_t)NT * NL * g.mr, (size_t)NT * NL * std::max(g.mr, h->reserve_m)));
       fat_kernel(h->st, FAT_BWD_OUTER, re.p, h->Q.p, g.mr, h->labels, h->P, h->Z.p, h->pred, h->stats_partial,
-                 h->nfat_blocks, NT);
+                 h->nfat_blocks, NT, h->dscal, h->ticket);
     }
     CKL();
-    reduce_stats(h->st, h->stats_partial, h->nfat_blocks, h->dscal);
-    CKL();
-    h->stats.launches += 2;
+    h->stats.launches += 1;
   }
   TRY(backward(h));
   CK(cudaMemcpyAsync(h->G.p + n, h->dscal, 16 * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
@@ -741,6 +736,7 @@ int tnml_create(int device, int flags, tnml_handle* out) {
   }
   h->nfat_blocks = fat_blocks(h->num_sm);
   if (cudaMalloc(&h->stats_partial, (size_t)h->nfat_blocks * 16 * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&h->ticket, 64) != cudaSuccess || cudaMemset(h->ticket, 0, 64) != cudaSuccess ||
       cudaMalloc(&h->dscal, 64 * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->dot_scratch, 1024 * sizeof(double)) != cudaSuccess ||
       cudaMallocHost(&h->hpin, 64 * sizeof(double)) != cudaSuccess) {
@@ -769,7 +765,7 @@ int tnml_destroy(tnml_handle h) {
   DBuf* bufs[] = {&h->B, &h->r, &h->p, &h->G, &h->T, &h->Gpart, &h->Q, &h->Z, &h->Bm};
   for (DBuf* b : bufs)
     if (b->p) cudaFree(b->p);
-  void* ptrs[] = {h->feat, h->labels, h->ones, h->P, h->PV, h->pred, h->stats_partial, h->dscal, h->dot_scratch,
+  void* ptrs[] = {h->feat, h->labels, h->ones, h->P, h->PV, h->pred, h->stats_partial, h->ticket, h->dscal, h->dot_scratch,
                   h->svd.X, h->svd.J, h->svd.sig2, h->svd.perm, h->svd.info, h->svd.flags,
                   h->svd.M, h->svd.tau, h->svd.ready, h->svd.Y, h->svd.M2, h->svd.tau2, h->svd.Y2, h->svd.perm0, h->svd.sweepmax};
   for (void* p : ptrs)

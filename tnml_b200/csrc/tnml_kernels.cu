@@ -427,11 +427,10 @@ static bool krgemm2_launch(cudaStream_t st, const double* In, long ldin, int ma,
     }
   }
   const int vec16 = ((ldin & 1) == 0 && (((size_t)In) & 15) == 0) ? 1 : 0;
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;   // one bit per device: function attributes are per device
+  if (first_on_device(attr)) {
     cudaFuncSetAttribute(krgemm2_kernel<S, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim);
     cudaFuncSetAttribute(krgemm2_kernel<S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim);
-    attr = true;
   }
   if (stages == 3)
     krgemm2_kernel<S, 3><<<X * P, 32 * G2_WARPS, bbytes + a3, st>>>(In, ldin, ma, f1, f2, div, Bm, ldb, J, Out, ldout,
@@ -472,11 +471,10 @@ void krgemm(cudaStream_t st, int S, const double* In, long ldin, int ma, const d
   }
   dim3 grid((unsigned)((rows + bm - 1) / bm), (unsigned)coltiles);
   size_t sh = (size_t)(2 * BK * LDA + 2 * BK * LDB) * sizeof(double);
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;   // one bit per device: function attributes are per device
+  if (first_on_device(attr)) {
     cudaFuncSetAttribute(krgemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(krgemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr = true;
   }
   if (S == 2)
     krgemm_kernel<2><<<grid, NTHR, sh, st>>>(In, ldin, ma, f1, f2, div, Bm, ldb, J, Out, ldout, rows, (int)bm);
@@ -719,22 +717,20 @@ void krgram(cudaStream_t st, int S, const double* In, long ldin, int ma, const d
   long rps = (rows + nsplit - 1) / nsplit;
   rps = ((rps + BK - 1) / BK) * BK;
   size_t sh = (size_t)(2 * BK * LDA + 2 * BK * LDB) * sizeof(double);
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;   // one bit per device: function attributes are per device
+  if (first_on_device(attr)) {
     cudaFuncSetAttribute(krgram_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(krgram_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr = true;
   }
   if (g_krgram_variant < 0) {   // TNML_KRGRAM=1: register-staged kernel only
     const char* e = getenv("TNML_KRGRAM");
     g_krgram_variant = e ? atoi(e) : 2;
   }
   if (S == 4 && g_krgram_variant == 2) {
-    static bool attr2 = false;
+    static unsigned long long attr2 = 0;   // one bit per device: function attributes are per device
     const size_t sh2 = (size_t)R2_STAGES * R2_STAGE_DOUBLES * sizeof(double);
-    if (!attr2) {
+    if (first_on_device(attr2)) {
       cudaFuncSetAttribute(krgram2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-      attr2 = true;
     }
     const int vecA = ((ldin & 1) == 0 && (((size_t)In) & 15) == 0) ? 1 : 0;
     const int vecZ = ((ldz & 1) == 0 && (((size_t)Z) & 15) == 0) ? 1 : 0;
@@ -767,16 +763,47 @@ __device__ __forceinline__ double warp_allsum(double v) {
   return v;
 }
 
+// Statistics of one pass (cost per label, #correct, sum |P|^2): every CTA leaves 16 partial sums,
+// the CTA that finishes last adds them up in a fixed order (deterministic, independent of which CTA
+// happens to be last) and resets the ticket.  Replaces the separate <<<1,512>>> reduce launch that
+// followed each of the 9 label-environment passes of a bond update (17 us each, cold).
+__device__ __forceinline__ void stats_finalize(const double* __restrict__ sp, int nblocks, double* __restrict__ stats,
+                                               unsigned* __restrict__ ticket) {
+  __shared__ int is_last;
+  __shared__ double part[8][16];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x < 128) {
+    const int i = threadIdx.x & 15, g = threadIdx.x >> 4;
+    double s = 0.0;
+    for (int b = g; b < nblocks; b += 8) s += __ldcg(sp + (long)b * 16 + i);
+    part[g][i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    double s = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) s += part[g][threadIdx.x];
+    stats[threadIdx.x] = s;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
 // MCH = ceil(m/32) <= 4: the image's whole fat environment (10 x m doubles) is loaded with
 // all loads in flight at once and stays in registers for the backward contraction (one HBM
 // read per image; the loop version below issued 11 loads per round trip and re-read F).
 // MCH = 0: generic loop version for m > 128.
 template <int MODE, int MCH>
-__global__ void __launch_bounds__(128, (MCH > 0) ? 3 : 4)
+__global__ void __launch_bounds__((MCH > 0) ? 384 : 512, 1)
 fat_kernel_t(const double* __restrict__ Q, const double* __restrict__ F, int m,
              const int32_t* __restrict__ labels, double* __restrict__ P, double* __restrict__ Z,
-             int32_t* __restrict__ pred, double* __restrict__ stats_partial, long NT) {
-  constexpr int WPB = 4;  // warps per block
+             int32_t* __restrict__ pred, double* __restrict__ stats_partial, long NT,
+             double* __restrict__ stats_out, unsigned* __restrict__ ticket) {
+  constexpr int WPB = (MCH > 0) ? 12 : 16;  // warps per block: one persistent CTA per SM
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long gw = (long)blockIdx.x * WPB + warp;
   const long nw = (long)gridDim.x * WPB;
@@ -915,6 +942,7 @@ fat_kernel_t(const double* __restrict__ Q, const double* __restrict__ F, int m,
       for (int w = 0; w < WPB; ++w) s += red[w][threadIdx.x];
     stats_partial[(long)blockIdx.x * 16 + threadIdx.x] = s;
   }
+  stats_finalize(stats_partial, gridDim.x, stats_out, ticket);
 }
 
 // ---------------------------------------------------------------------------
@@ -955,7 +983,8 @@ template <int MODE>
 __global__ void __launch_bounds__(512, 1)
 fat_bulk_kernel(const double* __restrict__ Q, const double* __restrict__ F, int m,
                 const int32_t* __restrict__ labels, double* __restrict__ P, double* __restrict__ Z,
-                int32_t* __restrict__ pred, double* __restrict__ stats_partial, int nblocks_stats, long NT) {
+                int32_t* __restrict__ pred, double* __restrict__ stats_partial, int nblocks_stats, long NT,
+                double* __restrict__ stats_out, unsigned* __restrict__ ticket) {
   constexpr bool GIVEN_P = (MODE == FAT_BWD);
   constexpr bool DO_Z = (MODE == FAT_GRAD || MODE == FAT_BWD);
   constexpr int C = 4;                       // m <= 128
@@ -1092,10 +1121,8 @@ fat_bulk_kernel(const double* __restrict__ Q, const double* __restrict__ F, int 
       for (int w = 0; w < wpb; ++w) s += red[w * 12 + threadIdx.x];
     stats_partial[(long)blockIdx.x * 16 + threadIdx.x] = s;
   }
-  // the statistics reducer sums nblocks_stats partials: clear the ones this grid does not own
-  for (long i = (long)gridDim.x * 16 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < (long)nblocks_stats * 16;
-       i += (long)gridDim.x * blockDim.x)
-    stats_partial[i] = 0.0;
+  (void)nblocks_stats;
+  stats_finalize(stats_partial, gridDim.x, stats_out, ticket);
 }
 
 static int g_fat_variant = -1;
@@ -1103,44 +1130,46 @@ void fat_set_variant(int v) { g_fat_variant = v; }
 
 template <int MODE>
 static bool fat_bulk_launch(cudaStream_t st, const double* Q, const double* F, int m, const int32_t* labels, double* P,
-                            double* Z, int32_t* pred, double* stats_partial, int nblocks, long NT) {
+                            double* Z, int32_t* pred, double* stats_partial, int nblocks, long NT, double* stats_out,
+                            unsigned* ticket) {
   if (m > 128 || m < 4) return false;
   const size_t per_warp = (size_t)2 * NL * m * sizeof(double);   // NBUF buffers
   int wpb = (int)((220 * 1024 - 512 - 16 * 12 * sizeof(double)) / per_warp);
   if (wpb > 16) wpb = 16;
   if (wpb < 4) return false;
-  const int grid = nblocks / 12;   // = number of SMs (fat_blocks): one persistent CTA per SM
+  const int grid = nblocks;        // = number of SMs (fat_blocks): one persistent CTA per SM
   if (grid < 1) return false;
   const size_t sh = 512 + 16 * 12 * sizeof(double) + (size_t)wpb * per_warp;
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;   // one bit per device: function attributes are per device
+  if (first_on_device(attr)) {
     cudaFuncSetAttribute(fat_bulk_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    attr = true;
   }
-  fat_bulk_kernel<MODE><<<grid, 32 * wpb, sh, st>>>(Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
+  fat_bulk_kernel<MODE><<<grid, 32 * wpb, sh, st>>>(Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT, stats_out,
+                                                    ticket);
   return true;
 }
 
-int fat_blocks(int num_sm) { return num_sm * 12; }
+int fat_blocks(int num_sm) { return num_sm; }
 
 template <int MODE>
 static void fat_launch(cudaStream_t st, const double* Q, const double* F, int m, const int32_t* labels, double* P,
-                       double* Z, int32_t* pred, double* sp, int nb, long NT) {
+                       double* Z, int32_t* pred, double* sp, int nb, long NT, double* so, unsigned* tk) {
   const int mch = (m + 31) / 32;
   if (mch == 1)
-    fat_kernel_t<MODE, 1><<<nb, 128, 0, st>>>(Q, F, m, labels, P, Z, pred, sp, NT);
+    fat_kernel_t<MODE, 1><<<nb, 384, 0, st>>>(Q, F, m, labels, P, Z, pred, sp, NT, so, tk);
   else if (mch == 2)
-    fat_kernel_t<MODE, 2><<<nb, 128, 0, st>>>(Q, F, m, labels, P, Z, pred, sp, NT);
+    fat_kernel_t<MODE, 2><<<nb, 384, 0, st>>>(Q, F, m, labels, P, Z, pred, sp, NT, so, tk);
   else if (mch == 3)
-    fat_kernel_t<MODE, 3><<<nb, 128, 0, st>>>(Q, F, m, labels, P, Z, pred, sp, NT);
+    fat_kernel_t<MODE, 3><<<nb, 384, 0, st>>>(Q, F, m, labels, P, Z, pred, sp, NT, so, tk);
   else if (mch == 4)
-    fat_kernel_t<MODE, 4><<<nb, 128, 0, st>>>(Q, F, m, labels, P, Z, pred, sp, NT);
+    fat_kernel_t<MODE, 4><<<nb, 384, 0, st>>>(Q, F, m, labels, P, Z, pred, sp, NT, so, tk);
   else
-    fat_kernel_t<MODE, 0><<<nb, 128, 0, st>>>(Q, F, m, labels, P, Z, pred, sp, NT);
+    fat_kernel_t<MODE, 0><<<nb, 512, 0, st>>>(Q, F, m, labels, P, Z, pred, sp, NT, so, tk);
 }
 
 void fat_kernel(cudaStream_t st, int mode, const double* Q, const double* F, int m, const int32_t* labels,
-                double* P, double* Z, int32_t* pred, double* stats_partial, int nblocks, long NT) {
+                double* P, double* Z, int32_t* pred, double* stats_partial, int nblocks, long NT, double* stats_out,
+                unsigned* ticket) {
   // Measured on B200 (bench.py, m = 120): the register-resident kernel streams the label environment
   // at 5.06 TB/s, the bulk-copy kernel at 4.77 TB/s with 2 buffers per warp (11 warps/SM) and
   // 4.70 TB/s with 3 (7 warps/SM): shared memory caps the bytes in flight at about the level the
@@ -1152,44 +1181,32 @@ void fat_kernel(cudaStream_t st, int mode, const double* Q, const double* F, int
   }
   if (g_fat_variant == 2 && NT >= 1024) {
     bool done = false;
-    if (mode == FAT_GRAD) done = fat_bulk_launch<FAT_GRAD>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
-    else if (mode == FAT_PAP) done = fat_bulk_launch<FAT_PAP>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
-    else if (mode == FAT_COST) done = fat_bulk_launch<FAT_COST>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
-    else if (mode == FAT_BWD) done = fat_bulk_launch<FAT_BWD>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
+    if (mode == FAT_GRAD) done = fat_bulk_launch<FAT_GRAD>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT, stats_out, ticket);
+    else if (mode == FAT_PAP) done = fat_bulk_launch<FAT_PAP>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT, stats_out, ticket);
+    else if (mode == FAT_COST) done = fat_bulk_launch<FAT_COST>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT, stats_out, ticket);
+    else if (mode == FAT_BWD) done = fat_bulk_launch<FAT_BWD>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT, stats_out, ticket);
     if (done) return;
   }
   switch (mode) {
     case FAT_GRAD:
-      fat_launch<FAT_GRAD>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
+      fat_launch<FAT_GRAD>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT, stats_out, ticket);
       break;
     case FAT_PAP:
-      fat_launch<FAT_PAP>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
+      fat_launch<FAT_PAP>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT, stats_out, ticket);
       break;
     case FAT_COST:
-      fat_launch<FAT_COST>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
+      fat_launch<FAT_COST>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT, stats_out, ticket);
       break;
     case FAT_BWD:
-      fat_launch<FAT_BWD>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
+      fat_launch<FAT_BWD>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT, stats_out, ticket);
       break;
     case FAT_BWD_OUTER:
-      fat_launch<FAT_BWD_OUTER>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
+      fat_launch<FAT_BWD_OUTER>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT, stats_out, ticket);
       break;
     default:
-      fat_launch<FAT_GRAD_OUTER>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT);
+      fat_launch<FAT_GRAD_OUTER>(st, Q, F, m, labels, P, Z, pred, stats_partial, nblocks, NT, stats_out, ticket);
       break;
   }
-}
-
-__global__ void reduce_stats_kernel(const double* __restrict__ sp, int nblocks, double* __restrict__ stats) {
-  // 16 warps, one per statistic: lanes stride over the per-block partials in a fixed order
-  const int lane = threadIdx.x & 31, i = threadIdx.x >> 5;
-  double s = 0.0;
-  for (int b = lane; b < nblocks; b += 32) s += sp[(long)b * 16 + i];
-  s = warp_allsum(s);
-  if (lane == 0) stats[i] = s;
-}
-void reduce_stats(cudaStream_t st, const double* sp, int nblocks, double* stats) {
-  reduce_stats_kernel<<<1, 512, 0, st>>>(sp, nblocks, stats);
 }
 
 // ---------------------------------------------------------------------------

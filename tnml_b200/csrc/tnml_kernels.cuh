@@ -10,6 +10,17 @@ namespace tnml {
 
 constexpr int NL = 10;
 
+// cudaFuncSetAttribute is per device: opt-ins are done once per device of the process (one handle
+// per GPU may live in the same process), tracked in a 64-bit mask owned by the call site.
+inline bool first_on_device(unsigned long long& mask) {
+  int d = 0;
+  cudaGetDevice(&d);
+  const unsigned long long bit = 1ull << (d & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 // ---- Khatri-Rao GEMM family -------------------------------------------------
 // krgemm: Out[row][j] = sum_{a,p} In[row][a] * w_p(img(row)) * Bm[(a*S+p)*ldb + j],  img(row) = row/div
 //   S = 2: w = (f1_0, f1_1) ; S = 4: w_{s*2+q} = f1_s * f2_q.  K = S*ma; the Khatri-Rao operand
@@ -44,13 +55,15 @@ enum FatMode : int {
   FAT_BWD_OUTER = 5,   // class C variant of FAT_BWD
 };
 // stats layout (double[16]): [0..9] cost per label, [10] ncorrect, [11] sum |P|^2
+// The statistics of the pass are reduced inside the launch (last CTA, fixed order) into stats_out[16];
+// `ticket` is a zero-initialised device counter owned by the caller.
 void fat_kernel(cudaStream_t st, int mode, const double* Q, const double* F, int m, const int32_t* labels,
-                double* P, double* Z, int32_t* pred, double* stats_partial, int nblocks, long NT);
+                double* P, double* Z, int32_t* pred, double* stats_partial, int nblocks, long NT, double* stats_out,
+                unsigned* ticket);
 int fat_blocks(int num_sm);
 // 1 (default): register-resident kernel; 2: bulk-async-copy (TMA, cp.async.bulk + mbarrier) double-buffered
 // kernel for m <= 128 from 1024 images on (measured slower: 4.77 vs 5.06 TB/s)
 void fat_set_variant(int v);
-void reduce_stats(cudaStream_t st, const double* stats_partial, int nblocks, double* stats /*[16]*/);
 
 // ---- small dense tensor helpers ---------------------------------------------
 // geometry of a bond-shaped tensor in its device ("canonical") layout
@@ -105,6 +118,8 @@ struct SvdWork {
   long capM2 = 0;
   int use_qr = -1;         // -1 auto, 0 never, 1 one QR, 3 sort + two QRs (TNML_SVD_QR)
   int hint_m = 0;          // largest link dimension expected (maxm): buffers are sized for it at once
+  int cluster_ok = -1;     // cluster-resident Jacobi usable on this handle's device (-1: not probed yet)
+  int cluster_checked = 0;
   cudaStream_t st2 = nullptr;              // side stream: the two apply-Q launches run concurrently
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // one Jacobi sweep captured as a CUDA graph, one executable per (buffers, dims) seen -- in a real

@@ -1659,13 +1659,12 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
   int Wd = 0;
   if (need16 <= 200 * 1024) Wd = 16;
   else if (need8 <= 200 * 1024) Wd = 8;
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;   // one bit per device: function attributes are per device
+  if (first_on_device(attr)) {
     cudaFuncSetAttribute(jacobi_offdiag_smem_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(jacobi_offdiag_smem_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(jacobi_diag_smem_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(jacobi_diag_smem_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
   }
   // Gram-based kernel: 2W staged columns of length rows+ns plus three (2W) x 36 matrices.
   // W = 8 by default: the round chain costs ~ W^3 per launch while a launch covers ~ W^2 pairs,
@@ -1677,6 +1676,9 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
     use_gram = e ? atoi(e) : 1;
     const char* ew = getenv("TNML_SVD_GRAM_W");
     if (ew && atoi(ew) == 16) gram_w = 16;
+  }
+  static unsigned long long attr_gram = 0;
+  if (first_on_device(attr_gram)) {
     cudaFuncSetAttribute(jacobi_gram_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     cudaFuncSetAttribute(jacobi_gram_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   }
@@ -1700,7 +1702,8 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
   const int max_sweeps = 60;
   int hflag = 0;
   // ---- cluster-resident path: all sweeps in one launch of a 16-CTA cluster (<= 256 columns)
-  static int use_cluster = -1;
+  // per handle (= per device): a device whose cluster launch is refused falls back alone
+  int& use_cluster = w.cluster_ok;
   if (use_cluster < 0) {
     const char* e = getenv("TNML_SVD_CLUSTER");
     use_cluster = e ? atoi(e) : 1;
@@ -1730,14 +1733,13 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
       at[0].val.clusterDim.z = 1;
       cfg.attrs = at;
       cfg.numAttrs = 1;
-      static int checked = 0;
-      if (!checked) {
+      if (!w.cluster_checked) {
         int ncl = 0;
         if (cudaOccupancyMaxActiveClusters(&ncl, jacobi_cluster_kernel<8>, &cfg) != cudaSuccess || ncl < 1) {
           cudaGetLastError();
           use_cluster = 0;
         }
-        checked = 1;
+        w.cluster_checked = 1;
       }
       if (use_cluster) {
         if (cudaMemsetAsync(w.sweepmax, 0, 64 * sizeof(double), st) != cudaSuccess) return -2;
@@ -1852,10 +1854,9 @@ static void launch_qr(cudaStream_t st, SvdWork& w, double* Xq, double* tau, int 
   qr_dataflow_kernel<RPL><<<(ns + 7) / 8, 256, 0, st>>>(Xq, nb, ns, tau, w.ready);
 }
 static void launch_qr_block8(cudaStream_t st, SvdWork& w, double* Xq, double* tau, int nb, int ns) {
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;   // one bit per device: function attributes are per device
+  if (first_on_device(attr)) {
     cudaFuncSetAttribute(qr_block_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-    attr = true;
   }
   size_t sh = (size_t)(32L * nb + 32) * sizeof(double) + 32 * sizeof(int);
   static long long* dbg = nullptr;
@@ -1911,10 +1912,9 @@ static int run_qr(cudaStream_t st, SvdWork& w, double* Xq, double* tau, int nb, 
   else if (nb <= 32 * 20) launch_qr<20>(st, w, Xq, tau, nb, ns);
   else if (nb <= 32 * 40) launch_qr<40>(st, w, Xq, tau, nb, ns);
   else {
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;   // one bit per device: function attributes are per device
+    if (first_on_device(attr)) {
       cudaFuncSetAttribute(qr_dataflow_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr = true;
     }
     qr_dataflow_smem_kernel<<<(ns + 7) / 8, 256, (size_t)8 * nb * sizeof(double), st>>>(Xq, nb, ns, tau, w.ready);
   }
@@ -1926,10 +1926,9 @@ static void run_apply_q(cudaStream_t st, const double* Xq, const double* tau, co
   else if (nb <= 32 * 20) launch_apply_q<20>(st, Xq, tau, src, perm, nb, ns, m, Yout, scale_sig2, rowperm);
   else if (nb <= 32 * 40) launch_apply_q<40>(st, Xq, tau, src, perm, nb, ns, m, Yout, scale_sig2, rowperm);
   else {
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;   // one bit per device: function attributes are per device
+    if (first_on_device(attr)) {
       cudaFuncSetAttribute(apply_q_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr = true;
     }
     apply_q_smem_kernel<<<(m + 7) / 8, 256, (size_t)8 * nb * sizeof(double), st>>>(Xq, tau, src, perm, nb, ns, m, Yout,
                                                                                scale_sig2, rowperm);
