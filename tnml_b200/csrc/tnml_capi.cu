@@ -119,6 +119,19 @@ struct tnml_handle_s {
   double* P = nullptr;  // [NT][NL]
   double* PV = nullptr; // [NT][NL]  p*v_n of the current CG pass (cg_reuse_forward)
   int cg_reuse_forward = 0;
+  // tcgen05 projection (tnml_ozaki.cu): int8 planes of the thin environment of the current bond
+  // (cut once per bond) and of the bond-shaped operand (cut per pass)
+  int8_t* oz_A8 = nullptr;
+  double* oz_ea = nullptr;
+  size_t oz_capA = 0, oz_capea = 0;
+  int8_t* oz_B8 = nullptr;
+  double* oz_eb = nullptr;
+  size_t oz_capB = 0, oz_capeb = 0;
+  long oz_tag_bond = -1, oz_tag_gen = -1;   // (bond, env generation) the planes in oz_A8 belong to
+  int oz_tag_ns = 0;
+  long env_gen = 0;                          // bumped whenever an environment slot is (re)written
+  int oz_slices = 8;                         // 8: float64-class accuracy (2^-57 of row max x column max)
+  int krgemm_variant = -1;                   // -1 default (3 where supported), 3 tcgen05, 2 DMMA persistent, 1 register-staged
   int reserve_m = 0;       // env slots are sized for this link dim (set from maxm by tnml_bond_update)
   // environment tiering: at most env_budget bytes of slots resident in HBM (0 = everything)
   cudaStream_t cp = nullptr;     // eviction stream (D2H) -- copies overlap the kernels and each other
@@ -419,6 +432,56 @@ int setup_geom(tnml_handle h, int b) {
   return 0;
 }
 
+int ensure_bytes(tnml_handle h, void** p, size_t& cap, size_t bytes) {
+  if (bytes <= cap) return 0;
+  if (*p) CK(cudaFreeAsync(*p, h->st));
+  *p = nullptr;
+  cap = 0;
+  CK(cudaMallocAsync(p, bytes, h->st));
+  cap = bytes;
+  return 0;
+}
+
+// Q[n][j] = sum_p w_p(n) sum_a thin[n][a] X[(a*4+p)*J + j]: the projection half of P = B * t.v
+// (fixedL.cc:318,377,399,416).  Default: tcgen05 int8 kernel on error-free 7-bit planes -- the planes
+// of the thin environment are cut once per bond (it does not change during the bond update), those
+// of X every call.  Fallback / variants 1,2: FP64 mma.sync kernels.
+int project(tnml_handle h, const double* thin, int mt, const double* f1, const double* f2, const double* X, int J) {
+  const long NT = h->NT;
+  int variant = h->krgemm_variant;
+  if (variant < 0) {
+    const char* e = getenv("TNML_KRGEMM");
+    variant = e ? atoi(e) : 3;
+  }
+  const int ns = h->oz_slices;
+  if (variant == 3 && NT >= 1024 && mt >= 48 && oz_supported(4, mt, ns)) {
+    const size_t wantA = oz_a8_bytes(NT, 8);
+    TRY(ensure_bytes(h, (void**)&h->oz_A8, h->oz_capA, wantA));
+    TRY(ensure_bytes(h, (void**)&h->oz_ea, h->oz_capea, (size_t)oz_rows_pad(NT) * sizeof(double)));
+    TRY(ensure_bytes(h, (void**)&h->oz_B8, h->oz_capB, oz_b8_bytes(4, J, 8)));
+    TRY(ensure_bytes(h, (void**)&h->oz_eb, h->oz_capeb, (size_t)oz_cols_pad(4, J) * sizeof(double)));
+    if (h->oz_tag_bond != h->currb || h->oz_tag_gen != h->env_gen || h->oz_tag_ns != ns) {
+      oz_slice_rows(h->st, thin, mt, mt, NT, ns, h->oz_A8, h->oz_ea);
+      CKL();
+      h->oz_tag_bond = h->currb;
+      h->oz_tag_gen = h->env_gen;
+      h->oz_tag_ns = ns;
+      h->stats.launches += 1;
+    }
+    oz_slice_cols(h->st, 4, X, J, mt, J, ns, h->oz_B8, h->oz_eb);
+    CKL();
+    if (oz_krgemm(h->st, 4, ns, h->oz_A8, h->oz_ea, NT, f1, f2, 1, h->oz_B8, h->oz_eb, J, h->Q.p, J, h->num_sm)) {
+      CKL();
+      h->stats.launches += 1;
+      return 0;
+    }
+    cudaGetLastError();   // tensor-map encoding unavailable: FP64 kernels below
+  }
+  krgemm(h->st, 4, thin, mt, mt, f1, f2, 1, X, J, J, h->Q.p, J, NT, h->num_sm);
+  CKL();
+  return 0;
+}
+
 // forward pass: P[n][l] for bond-shaped tensor X (canonical layout).
 // mode: FAT_GRAD (also produces Z), FAT_PAP, FAT_COST.  Leaves stats in dstats.
 int forward(tnml_handle h, const double* X, int mode, double* dstats, double* Pout = nullptr) {
@@ -441,8 +504,7 @@ int forward(tnml_handle h, const double* X, int mode, double* dstats, double* Po
     if (mode == FAT_GRAD) TRY(ensure(h, h->Z, (size_t)NT * mf, wantq));
     {
       PhaseTimer t(h, PH_PROJ);
-      krgemm(h->st, 4, thin.p, mt, mt, fth, ffa, 1, X, mf, mf, h->Q.p, mf, NT, h->num_sm);
-      CKL();
+      TRY(project(h, thin.p, mt, fth, ffa, X, mf));
     }
     {
       PhaseTimer t(h, PH_FAT);
@@ -460,8 +522,7 @@ int forward(tnml_handle h, const double* X, int mode, double* dstats, double* Po
     if (mode == FAT_GRAD) TRY(ensure(h, h->Z, (size_t)NT * J, wantq));
     {
       PhaseTimer t(h, PH_PROJ);
-      krgemm(h->st, 4, le.p, g.ml, g.ml, featp(h, b), featp(h, b + 1), 1, X, J, (int)J, h->Q.p, J, NT, h->num_sm);
-      CKL();
+      TRY(project(h, le.p, g.ml, featp(h, b), featp(h, b + 1), X, (int)J));
     }
     {
       PhaseTimer t(h, PH_FAT);
@@ -674,6 +735,7 @@ int advance_env(tnml_handle h, int c, int right) {
   ns.m = kout;
   ns.fat = outfat;
   ns.kind = right ? 2 : 1;
+  ++h->env_gen;
   return 0;
 }
 
@@ -766,6 +828,7 @@ int tnml_destroy(tnml_handle h) {
   for (DBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   void* ptrs[] = {h->feat, h->labels, h->ones, h->P, h->PV, h->pred, h->stats_partial, h->ticket, h->dscal, h->dot_scratch,
+                  h->oz_A8, h->oz_ea, h->oz_B8, h->oz_eb,
                   h->svd.X, h->svd.J, h->svd.sig2, h->svd.perm, h->svd.info, h->svd.flags,
                   h->svd.M, h->svd.tau, h->svd.ready, h->svd.Y, h->svd.M2, h->svd.tau2, h->svd.Y2, h->svd.perm0, h->svd.sweepmax};
   for (void* p : ptrs)
@@ -824,6 +887,7 @@ int tnml_set_images(tnml_handle h, int64_t NT, int N, const double* feat, const 
   h->W.assign(N + 2, Site());
   h->currb = -1;
   h->bond_valid = false;
+  ++h->env_gen;
   const size_t nf = (size_t)(N + 2) * NT * 2;
   CK(cudaMalloc(&h->feat, nf * sizeof(double)));
   CK(cudaMalloc(&h->labels, NT * sizeof(int32_t)));
@@ -1242,8 +1306,14 @@ int tnml_set_option(tnml_handle h, const char* name, double value) {
     krgram_set_variant((int)value);
     return TNML_OK;
   }
-  if (strcmp(name, "krgemm_variant") == 0) {   // process-wide (testing / A-B timing)
-    krgemm_set_variant((int)value);
+  if (strcmp(name, "krgemm_variant") == 0) {   // per handle: 3 tcgen05 int8 (default), 2 DMMA persistent, 1 register-staged
+    h->krgemm_variant = (int)value;
+    krgemm_set_variant((int)value == 1 ? 1 : -1);   // the environment advance follows variant 1 (process-wide switch)
+    return TNML_OK;
+  }
+  if (strcmp(name, "oz_slices") == 0) {
+    if (value < 6 || value > 8) return fail(h, TNML_ERR_INVALID, "oz_slices must be 6, 7 or 8");
+    h->oz_slices = (int)value;
     return TNML_OK;
   }
   if (strcmp(name, "env_budget_gb") == 0) {

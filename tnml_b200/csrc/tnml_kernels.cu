@@ -451,7 +451,7 @@ void krgemm(cudaStream_t st, int S, const double* In, long ldin, int ma, const d
     const char* e = getenv("TNML_KRGEMM");
     g_krgemm_variant = e ? atoi(e) : 2;
   }
-  if (g_krgemm_variant == 2 && rows >= 512) {
+  if (g_krgemm_variant >= 2 && rows >= 512) {   // (3 = tcgen05 projection, chosen by the caller; here it means 2)
     const bool ok = (S == 2) ? krgemm2_launch<2>(st, In, ldin, ma, f1, f2, div, Bm, ldb, J, Out, ldout, rows, num_sm)
                              : krgemm2_launch<4>(st, In, ldin, ma, f1, f2, div, Bm, ldb, J, Out, ldout, rows, num_sm);
     if (ok) return;

@@ -33,6 +33,23 @@ void krgemm(cudaStream_t st, int S, const double* In, long ldin, int ma, const d
 // resident B panel (from 512 rows on, while the panel fits); 1: register-staged kernel only
 void krgemm_set_variant(int v);
 
+// ---- the same projection on tcgen05 (tnml_ozaki.cu): int8 error-free splitting, TMA, TMEM -------------
+// Operands are cut into `ns` signed 7-bit planes once (rows of In: per environment, i.e. once per
+// bond; columns of Bm: per CG pass) and multiplied exactly by tcgen05.mma kind::i8.
+bool oz_supported(int S, int ma, int ns);                 // S in {2,4}, ma <= 128, ns in 6..8
+size_t oz_a8_bytes(long rows, int ns);                    // plane buffer of the row operand
+long oz_rows_pad(long rows);                              // entries of ea[]
+size_t oz_b8_bytes(int S, int J, int ns);                 // plane buffer of the column operand
+long oz_cols_pad(int S, int J);                           // entries of eb[]
+void oz_slice_rows(cudaStream_t st, const double* In, long ldin, int ma, long rows, int ns, int8_t* A8, double* ea);
+void oz_slice_cols(cudaStream_t st, int S, const double* Bm, long ldb, int ma, int J, int ns, int8_t* B8, double* eb);
+// Out[row][j] = sum_p w_p(row/div) sum_a In[row][a] Bm[(a*S+p)*ldb + j]; false: not launched
+bool oz_krgemm(cudaStream_t st, int S, int ns, const int8_t* A8, const double* ea, long rows, const double* f1,
+               const double* f2, int div, const int8_t* B8, const double* eb, int J, double* Out, long ldout,
+               int num_sm);
+
+void oz_set_debug_buffer(long long* dev_buf);               // -DOZ_PROFILE builds only: [CTA][8] cycle counters
+
 // krgram: Gpart[split][(a*S+p)][j] = sum_{row in split} In[row][a] * w_p(row) * Z[row][j]
 // The rank-1 gradient accumulation of fixedL.cc:379,418 as one K=NT contraction, split-K over
 // CTAs, partials reduced in a fixed order (deterministic).
