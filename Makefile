@@ -33,9 +33,11 @@ clean:
 .PHONY: all lib host oracle clean
 
 # micro-benchmarks behind the design decisions (run on the GPU box)
-TOOLS := tools/dmma_bench tools/dmma_lds_bench tools/imma_bench tools/lat_bench tools/krgemm_bench_base
+TOOLS := tools/dmma_bench tools/dmma_lds_bench tools/imma_bench tools/lat_bench tools/krgemm_bench_base tools/umma_bench tools/oz_test
 tools: $(TOOLS)
 tools/krgemm_bench_base: tools/krgemm_bench.cu $(CSRC)
 	$(NVCC) -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o $@ $<
+tools/oz_test: tools/oz_test.cu tnml_b200/csrc/tnml_ozaki.cu tnml_b200/csrc/tnml_kernels.cu tnml_b200/csrc/tnml_kernels.cuh
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o $@ tools/oz_test.cu tnml_b200/csrc/tnml_ozaki.cu tnml_b200/csrc/tnml_kernels.cu
 tools/%: tools/%.cu
 	$(NVCC) -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o $@ $<

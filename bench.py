@@ -34,12 +34,25 @@ def parse():
     ap.add_argument("--maxm", type=int, default=120)
     ap.add_argument("--npass", type=int, default=4)
     ap.add_argument("--first-bond", type=int, default=10)
-    ap.add_argument("--cpu-sample", type=int, default=1024, help="images in the CPU-baseline sample")
+    ap.add_argument("--config", type=int, default=3, choices=[3, 5],
+                    help="BASELINE config: 3 (= 4 with --gpus N; default) full-MNIST-shaped 60000 x 196 sites, maxm=120; "
+                         "5: synthetic 1e6 images, maxm=300, window of bonds on an 8-site chain")
+    ap.add_argument("--cpu-sample", type=int, default=1024, help="images in the CPU-baseline sample (literal dense t.v)")
+    ap.add_argument("--cpu-sample-structured", type=int, default=4000,
+                    help="images in the structured (Khatri-Rao form, BLAS) CPU-baseline sample")
+    ap.add_argument("--sweep-avg", type=int, default=1, help="1: also time one full sweep (config 3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cg-reuse-forward", type=int, default=0,
                     help="1: linear update of the forward outputs between CG passes (tnml_set_option); "
                          "0 (default): literal recompute like fixedL.cc:412-421")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.config == 5:
+        if a.nt == 60000:
+            a.nt = 1000000
+        if a.maxm == 120:
+            a.maxm = 300
+        a.first_bond = 2
+    return a
 
 
 # ---------------------------------------------------------------------------
@@ -49,6 +62,55 @@ def load_peaks():
         j = json.load(open(p))
         return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_tensor_peaks():
+    """Tensor-pipe peaks measured on THIS box right before the timed run (rank 0): the FP64 DMMA pipe
+    (tools/dmma_bench) and the tcgen05 int8 pipe at the clock the power cap allows (tools/umma_bench).
+    MEASURED_PEAKS.json (driver-written) holds only HBM and bf16; both are recorded next to these."""
+    out = {}
+    pj = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pj):
+        j = json.load(open(pj))
+        out["bf16_tflops_file"] = float(j.get("bf16_tflops", 0.0))
+        out["bf16_tflops_sustained_file"] = float(j.get("bf16_tflops_sustained", 0.0))
+        out["hbm_gbs_file"] = float(j.get("hbm_gbs", 0.0))
+    import re
+    exe = os.path.join(ROOT, "tools", "dmma_bench")
+    if os.path.exists(exe):
+        try:
+            o = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
+            mt = re.search(r"dmma only.*?DMMA ([0-9.]+) TF/s", o)
+            if mt:
+                out["dmma_tflops"] = float(mt.group(1))
+                out["dmma_src"] = "tools/dmma_bench in this run (mma.sync.m8n8k4.f64, all SMs)"
+        except Exception:
+            pass
+    exe = os.path.join(ROOT, "tools", "umma_bench")
+    if os.path.exists(exe):
+        try:
+            o = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
+            mt = re.search(r"INT8_PEAK_TOPS ([0-9.]+).*?SM clock ([0-9.]+) MHz", o)
+            if mt:
+                out["int8_tops"] = float(mt.group(1))
+                out["int8_sm_mhz"] = float(mt.group(2))
+                out["int8_src"] = ("tools/umma_bench in this run: tcgen05.mma kind::i8 M=128 N=256 back to back on all SMs, "
+                                   "wall clock (power-capped SM clock %.0f MHz)" % float(mt.group(2)))
+        except Exception:
+            pass
+    return out
+
+
+def load_traffic(NT):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture of this round
+    (profiles/r02_ncu_summary.json, written by tools/make_profiles.py with the commit it was taken at);
+    captured at a smaller NT (ncu replays every kernel ~40 times) and scaled linearly in NT."""
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_summary.json")))
+        k = j["kernels"]["oz_gemm"]
+        return float(k["dram_bytes"]) * (NT / float(k["NT"])), f"ncu --set full at NT={k['NT']} (commit {j.get('commit', '?')}), scaled"
+    except Exception:
+        return None, "no ncu capture of this round committed yet"
 
 
 class ClockSampler:
@@ -127,15 +189,45 @@ class ClockSampler:
                 "samples": len(self.rows), "how": self.how}
 
 
+def chain_geometry(args):
+    """(N sites, first / last saturated class-L bond, bonds of one timed excursion builder)."""
+    if args.config == 5:
+        return 8
+    return 196
+
+
 def build_workload(args, rank, world):
-    """Synthetic config-3 shaped inputs for this rank's shard."""
+    """Synthetic inputs for this rank's shard (ParallelDo bounds of the global image list)."""
     from tnml_b200 import data, fixedl
     NTg = args.nt
     b0, b1 = fixedl.bounds(world, NTg)[rank]
+    if args.config == 5:
+        pix, labels = data.synthetic_pixels(b1 - b0, 8, seed=20260925, first=b0)
+        feat = data.phi(pix * 255.0)
+        W = data.window_mps(8, 2, args.maxm, seed=5)
+        return feat, labels, W, NTg, b0
     pix, labels = data.synthetic_digits(b1 - b0, 14, seed=20260925, first=b0)
     feat = data.phi(pix)                      # [NT, 196, 2] = TState::data
     W = data.random_mps(196, 2, args.maxm, seed=3)
     return feat, labels, W, NTg, b0
+
+
+def excursion(args, K):
+    """Bond schedule of one timed pass of K bond updates that returns to its starting state, so that
+    the pass can be repeated (main / breakdown / end-to-end / cg_reuse_forward passes).
+    config 3: class-L bonds with m_l = m_r = maxm: ceil(K/2) bonds rightwards from first_bond (ha=1), then
+    floor(K/2) leftwards back (ha=2; the turning bond is optimised twice in a row like sweepnext does at
+    the chain end, fixedL.cc:470-476): rightward bonds advance a thin environment, leftward ones the
+    label-carrying one (kappa = 10), so both halves of a sweep are in the figure.
+    config 5: the window 2..6 of the 8-site chain (class L, C, C, R, R) rightwards then leftwards."""
+    if args.config == 5:
+        cyc = [(b, 1) for b in range(2, 7)] + [(b, 2) for b in range(6, 1, -1)]
+        return [cyc[k % len(cyc)] for k in range(K)]
+    lo = args.first_bond
+    nr = (K + 1) // 2
+    right = [(lo + k, 1) for k in range(nr)]
+    left = [(lo + nr - 1 - k, 2) for k in range(K - nr)]
+    return right + left
 
 
 def cpu_baseline(args, steps=1):
@@ -174,11 +266,89 @@ def cpu_baseline(args, steps=1):
             "host_cpus": os.cpu_count()}, t
 
 
+def cpu_baseline_structured(args):
+    """BASELINE.md variant (ii): the best-case CPU formulation -- the same Khatri-Rao-structured
+    contractions the GPU path uses, as BLAS GEMMs (numpy/OpenBLAS, all host cores) in the oracle -- one
+    whole bond update (cgrad + svd + quadcost + shiftE) on a sample of the images, scaled linearly in NT
+    (the SVD, which does not scale with NT, is timed separately and added unscaled)."""
+    from oracle import fixedl_oracle as O           # checker / baseline only
+    from tnml_b200 import data
+    ns = min(args.cpu_sample_structured, args.nt)
+    if args.config == 5:
+        pix, labels = data.synthetic_pixels(ns, 8, seed=20260925)
+        feat = O.features(pix)
+        W = data.window_mps(8, 2, args.maxm, seed=5)
+        b = 2
+    else:
+        # a class-L bond with ml = mr = maxm costs the same on a 24-site chain as on the 196-site one;
+        # the short chain keeps the (untimed) environment set-up of the sample small
+        pix, labels = data.synthetic_digits(ns, 14, seed=20260925)
+        feat = O.features(pix[:, 86:86 + 24])
+        W = data.random_mps(24, 2, args.maxm, seed=3)
+        b = 10
+    chunk = 1000
+    tss = [O.TrainStates(feat[a:a + chunk], labels[a:a + chunk].astype(np.int64)) for a in range(0, ns, chunk)]
+    for t in tss:
+        t.init(W)
+        for bb in range(1, b):
+            t.set_bond(bb)
+            t.shiftE(W, bb, "Fromleft")
+        t.set_bond(b)
+    B = O.form_bond(W[b], W[b + 1])
+    jc = tss[0].jc
+
+    def grad(X):
+        G, C = np.zeros_like(X), 0.0
+        for t in tss:
+            g, c = O._grad(X, t, 0.0, False)
+            G, C = G + g, C + c
+        return G, C
+    t0 = time.perf_counter()
+    r, _ = grad(B)
+    p_ = r.copy()
+    for ps in range(1, args.npass + 1):
+        pAp = sum(float(np.sum(O.project(p_, t) ** 2)) for t in tss)
+        B = B + (float(np.sum(r * r)) / pAp) * p_
+        if ps == args.npass:
+            break
+        nr, _ = grad(B)
+        beta = float(np.sum(nr * nr)) / float(np.sum(r * r))
+        r = nr
+        p_ = r + beta * p_
+    t_cg = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    Wb, Wb1, m, te = O.svd_split(B, b, 1, jc, args.maxm, max(10, args.maxm // 2), 1e-10)
+    t_svd = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    newB = O.form_bond(Wb, Wb1)
+    for t in tss:
+        O.quadcost(newB, t)
+    Wn = list(W)
+    Wn[b], Wn[b + 1] = Wb, Wb1
+    for t in tss:
+        t.shiftE(Wn, b, "Fromleft")
+    t_rest = time.perf_counter() - t0
+    t_full = (t_cg + t_rest) * args.nt / ns + t_svd
+    return {"value": 1.0 / t_full, "unit": "bond-updates/sec", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{ns} images, one whole class-L bond update at ml=mr={args.maxm} in the structured (Khatri-Rao, BLAS GEMM) "
+                      f"form of the numpy oracle: cgrad {t_cg:.2f} s + quadcost/shiftE {t_rest:.2f} s scaled linearly to "
+                      f"NT={args.nt}, + LAPACK svd {t_svd:.3f} s unscaled; numpy/OpenBLAS threads = host cores"}
+
+
 def config_dict(args, world):
-    return {"workload": "BASELINE config 3/4: synthetic 14x14 MNIST-shaped, N=196 sites d=2 NL=10, "
-                        f"NT={args.nt} images total, maxm={args.maxm} minm={max(10, args.maxm // 2)} "
-                        f"Npass={args.npass} cutoff=1e-10, bonds {args.first_bond}.. (class L, ml=mr={args.maxm})",
-            "NT_total": args.nt, "N": 196, "maxm": args.maxm, "Npass": args.npass, "cg_reuse_forward": int(getattr(args, "cg_reuse_forward", 0)),
+    if args.config == 5:
+        wl = ("BASELINE config 5: synthetic hash-RNG pixels, d=2 NL=10, "
+              f"NT={args.nt} images total, maxm=minm={args.maxm} Npass={args.npass}, window of bonds 2..6 (class L, C, C, R, R; "
+              f"rightwards then leftwards) of an 8-site chain with link dimension {args.maxm} on every bond")
+        N = 8
+    else:
+        wl = ("BASELINE config 3/4: synthetic 14x14 MNIST-shaped, N=196 sites d=2 NL=10, "
+              f"NT={args.nt} images total, maxm={args.maxm} minm={max(10, args.maxm // 2)} "
+              f"Npass={args.npass} cutoff=1e-10, class-L bonds with ml=mr={args.maxm}: half of the steps rightwards from bond "
+              f"{args.first_bond}, half leftwards back")
+        N = 196
+    return {"workload": wl,
+            "NT_total": args.nt, "N": N, "maxm": args.maxm, "Npass": args.npass, "cg_reuse_forward": int(getattr(args, "cg_reuse_forward", 0)),
             "parallelism": f"dp{world} (images sharded, NCCL all-reduce of the bond gradient)" if world > 1 else "dp1",
             "l2": "per-bond inputs (environment cache, >=600 MB/rank at NT=60000) exceed the 126 MB L2; no flush needed"}
 
@@ -188,7 +358,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, t = cpu_baseline(args, steps=max(1, min(args.steps, 2)))
+    if args.config == 5:      # dense t.v at m=300 is 29 MB per image: only the structured form is runnable
+        base = cpu_baseline_structured(args)
+    else:
+        base, t = cpu_baseline(args, steps=max(1, min(args.steps, 2)))
     line = {"impl": "reference", "metric": "bond-updates/sec", "value": base["value"], "unit": "bond-updates/sec",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 / base["value"], "higher_is_better": True, "scaling": "strong",
@@ -234,7 +407,7 @@ def run_ours(args):
     h.synchronize()
     setup_s = time.perf_counter() - t_setup0
 
-    minm = max(10, args.maxm // 2)
+    minm = args.maxm if args.config == 5 else max(10, args.maxm // 2)
     p = capi.BondParams(args.npass, 0.0, 1e-10, 1e-10, args.maxm, minm, 0)
     ext = torch.cuda.ExternalStream(h.stream(), device=torch.device("cuda", local))
 
@@ -245,39 +418,21 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # Bond schedule: class-L bonds with m_l = m_r = maxm only, b = first_bond .. jc-2 going right,
-    # then bouncing inside that range like sweepnext does at the chain ends (the turning bond is
-    # optimised twice in a row, fixedL.cc:470-476) so that any --steps K can be served.
-    lo, hi = b0, 196 // 2 - 2
-
-    def schedule():
-        b, ha = lo, 1
-        while True:
-            yield b, ha
-            if ha == 1:
-                if b == hi:
-                    ha = 2
-                else:
-                    b += 1
-            else:
-                if b == lo:
-                    ha = 1
-                else:
-                    b -= 1
-    sched = schedule()
-    visited = []
-
     def timed(nsteps, e2e=False):
-        """K bond updates; device time by CUDA events on the library's stream."""
+        """One excursion of nsteps bond updates (it returns to the starting state); device time by CUDA
+        events on the library's stream, also for the rightward and the leftward half."""
+        sched = excursion(args, nsteps)
         res = []
         h2d = d2h = 0
         barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        turn = next((k for k, (_, ha) in enumerate(sched) if ha == 2), len(sched))
         with torch.cuda.stream(ext):
-            ev0.record()
-        for k in range(nsteps):
-            b, ha = next(sched)
-            visited.append(b)
+            ev[0].record()
+        for k, (b, ha) in enumerate(sched):
+            if k == turn:
+                with torch.cuda.stream(ext):
+                    ev[1].record()
             if e2e:   # the host owns the MPS (like the reference's `W`): sites go H2D, results D2H
                 for j in (b, b + 1):
                     Wj = h.get_site(j) if Whost.get(j) is None else Whost[j]
@@ -291,18 +446,23 @@ def run_ours(args):
                 d2h += 8 * 40
             res.append(r)
         with torch.cuda.stream(ext):
-            ev1.record()
+            if turn >= len(sched):
+                ev[1].record()
+            ev[2].record()
         barrier()
-        ms = ev0.elapsed_time(ev1)
+        ms = [ev[0].elapsed_time(ev[2]), ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])]
         if dist is not None:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            t = torch.tensor(ms, device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, res, h2d, d2h
+            ms = [float(x) for x in t.tolist()]
+        return ms, res, h2d, d2h, sched
 
     K, Wm = args.steps, max(args.warmup, 3)
+    if args.config == 5:          # whole window sweeps only (the excursion must return to its start)
+        K = max(10, ((K + 9) // 10) * 10)
+        Wm = 10
     Whost = {}
-    ms, _, _, _ = timed(Wm)                           # warm-up
+    timed(Wm)                                         # warm-up
     uuid = None
     try:
         uuid = "GPU-" + str(torch.cuda.get_device_properties(local).uuid)
@@ -312,95 +472,145 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     h.stats(reset=True)
-    ms, res, _, _ = timed(K)
+    ms3, res, _, _, sched = timed(K)
     st = h.stats(reset=True)
     clocks = sampler.finish() if rank == 0 else None
+    ms = ms3[0]
     value = K / (ms / 1000.0)
-    timed_bonds = visited[Wm:Wm + K]
+    n_right = sum(1 for (_, ha) in sched if ha == 1)
+    n_left = K - n_right
 
     # breakdown pass with per-phase CUDA events (on the library's stream)
     h.set_timing(True)
-    ms_t, res_t, _, _ = timed(K)
+    _, res_t, _, _, _ = timed(K)
     stt = h.stats(reset=True)
     h.set_timing(False)
 
     # end-to-end pass: host-resident MPS, site tensors cross PCIe every step.  The host copies of
     # the sites the pass will touch are fetched before the timed region (they are inputs).
-    for j in range(lo, hi + 2):
+    for j in sorted({x for (b, _) in sched for x in (b, b + 1)}):
         Whost[j] = h.get_site(j)
-    ms_e, res_e, h2d, d2h = timed(K, e2e=True)
-    e2e_value = K / (ms_e / 1000.0)
+    mse, res_e, h2d, d2h, _ = timed(K, e2e=True)
+    e2e_value = K / (mse[0] / 1000.0)
 
     value_reuse = None
     if not args.cg_reuse_forward:
         h.set_option("cg_reuse_forward", 1)
-        ms_r, _, _, _ = timed(K)
+        msr, _, _, _, _ = timed(K)
         h.set_option("cg_reuse_forward", 0)
-        value_reuse = K / (ms_r / 1000.0)
+        value_reuse = K / (msr[0] / 1000.0)
+
+    # one FULL sweep (2(N-1) bond updates incl. the cheap edge bonds and the expensive class-C bonds)
+    # from the initial MPS: the user-visible sweep-average rate next to the saturated-bond rate above
+    sweep_avg = None
+    if args.sweep_avg and args.config == 3:
+        h.set_mps(W)
+        h.init_envs()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ext):
+            e0.record()
+        nb = 0
+        last = None
+        for b, ha in fixedl.sweepnext(196):
+            last = h.bond_update(b, ha, p)
+            nb += 1
+        with torch.cuda.stream(ext):
+            e1.record()
+        barrier()
+        mss = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([mss], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            mss = float(t.item())
+        sweep_avg = {"value": nb / (mss / 1000.0), "unit": "bond-updates/sec", "bond_updates": nb, "seconds": mss / 1000.0,
+                     "note": "one full sweep b=1..195..1 from the initial random MPS (link dims min(2^j, 2^(N-j), maxm)): "
+                             "includes the small edge bonds and the four class-C bonds (label index on the bond tensor)",
+                     "final_cost_per_image": last.cost / NTg}
 
     if rank == 0:
         peak, peak_src = load_peaks()
+        peaks = measured_tensor_peaks()
         NT = feat.shape[0]
         m = args.maxm
-        # CUDA-event breakdown (events recorded on the library's own stream by tnml_set_timing)
-        phases = {"proj(krgemm)": stt.ms_proj, "grad(krgram+reduce)": stt.ms_grad, "fat": stt.ms_fat,
+        phases = {"proj(slice+oz_gemm)": stt.ms_proj, "grad(krgram+reduce)": stt.ms_grad, "fat": stt.ms_fat,
                   "svd": stt.ms_svd, "shift": stt.ms_shift, "other": stt.ms_other}
         dom = max(phases, key=phases.get)
         npass = args.npass
         reuse = int(args.cg_reuse_forward)
-        n_gemm = ((npass + 2) if reuse else (2 * npass + 1)) * K   # krgemm launches in K bond updates
+        nclsL = sum(1 for (b, _) in sched if not (args.config == 5 and b in (3, 4)))   # class L/R bond updates
+        n_gemm = ((npass + 2) if reuse else (2 * npass + 1)) * K   # projection launches in K bond updates
         n_fwd = (2 * npass + 1) * K          # fat-kernel launches (passes over the fat environment)
         n_bwd = npass * K                    # krgram launches
-        # --- dominant data-parallel kernel: krgemm2_kernel<4,3> (FP64 tensor-core MMAs, DMMA.8x8x4)
-        # algorithmic flops per launch = 2 * NT * (4*m_l) * m_r  (8 m_l m_r per image)
+        # --- dominant data-parallel kernel: oz_gemm_kernel<8,4> (tcgen05.mma kind::i8, TMA, TMEM)
+        # algorithmic float64 work per launch = 2 * NT * (4 m_l) * m_r flop (8 m_l m_r per image);
+        # executed tensor work = 36 exact int8 slice products on K padded to 128: 2 * NTpad * 128 * 4 m_r * 36 ops
         gemm_flops_launch = 8.0 * NT * m * m
-        gemm_ms_launch = stt.ms_proj / max(1, n_gemm)
-        gemm_tf = gemm_flops_launch / (gemm_ms_launch / 1000.0) / 1e12 if gemm_ms_launch > 0 else 0.0
-        FP64_TENSOR_PEAK = 37.0   # TF/s, measured on this pool with tools/dmma_bench.cu (DMMA and DFMA share it)
-        traffic = None
-        try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))["kernels"]["krgemm2"]
-            rd = float(prof["dram__bytes_read.sum"].split()[0]) * (1e6 if "Mbyte" in prof["dram__bytes_read.sum"] else 1e3)
-            wr = float(prof["dram__bytes_write.sum"].split()[0]) * (1e6 if "Mbyte" in prof["dram__bytes_write.sum"] else 1e3)
-            traffic = (rd + wr) * (NT / 30000.0)       # captured at NT=30000 (ncu cannot replay 62 GB), linear in NT
-        except Exception:
-            pass
-        roof = {"bound": "tensor", "kernel": "krgemm2_kernel<4,3> (Khatri-Rao projection GEMM, FP64 mma.sync m8n8k4, "
-                                            "cp.async-staged, persistent)",
-                "achieved": gemm_tf, "peak": FP64_TENSOR_PEAK, "unit": "TFLOP/s", "frac": gemm_tf / FP64_TENSOR_PEAK,
-                "traffic": traffic,
-                "peak_source": "FP64 tensor/FMA pipe measured with tools/dmma_bench.cu on this pool's B200 (37.0 TF/s); "
-                               "MEASURED_PEAKS.json holds bf16 and HBM only -- the path computes in f64 (DESIGN.md 3)",
-                "launch_avg_ms": gemm_ms_launch, "launches_in_region": n_gemm,
-                "algorithmic_flops_per_launch": gemm_flops_launch,
-                "phase_ms_per_step": {k: v / K for k, v in phases.items()}, "dominant_phase": dom}
+        ntp = ((NT + 127) // 128) * 128
+        gemm_int8_ops_launch = 2.0 * ntp * 128.0 * (4.0 * ((m + 7) // 8) * 8) * 36.0
+        gemm_ms_launch = stt.ms_proj / max(1, n_gemm)     # includes the plane cutting (once per bond + once per launch)
+        tops = gemm_int8_ops_launch / (gemm_ms_launch / 1000.0) / 1e12 if gemm_ms_launch > 0 else 0.0
+        i8_peak = peaks.get("int8_tops") or 2.0 * peaks.get("bf16_tflops_file", 0.0)
+        traffic, traffic_src = load_traffic(NT)
+        tc_path = (m <= 128 and NT >= 1024)
+        if tc_path:
+            roof = {"bound": "tensor", "kernel": "oz_gemm_kernel<8,4> (Khatri-Rao projection GEMM as 36 exact int8 slice products: "
+                                                "tcgen05.mma kind::i8 + TMA + TMEM, float64-class result)",
+                    "achieved": tops, "peak": i8_peak, "unit": "TOP/s (int8 tensor ops executed; TFLOP/s-equivalent below)",
+                    "frac": tops / i8_peak if i8_peak else None, "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": peaks.get("int8_src", "2 x MEASURED_PEAKS.json bf16_tflops (int8 rate = 2 x bf16 on this part)"),
+                    "fp64_equiv_tflops": gemm_flops_launch / (gemm_ms_launch / 1000.0) / 1e12 if gemm_ms_launch > 0 else 0.0,
+                    "fp64_dmma_pipe_tflops": peaks.get("dmma_tflops"),
+                    "launch_avg_ms": gemm_ms_launch, "launches_in_region": n_gemm,
+                    "algorithmic_flops_per_launch": gemm_flops_launch, "int8_ops_per_launch": gemm_int8_ops_launch,
+                    "phase_ms_per_step": {k: v / K for k, v in phases.items()}, "dominant_phase": dom}
+        else:
+            gemm_tf = gemm_flops_launch / (gemm_ms_launch / 1000.0) / 1e12 if gemm_ms_launch > 0 else 0.0
+            dpk = peaks.get("dmma_tflops") or 37.0
+            roof = {"bound": "tensor", "kernel": "krgemm_kernel / krgemm2_kernel (FP64 mma.sync m8n8k4; link dimension > 128: "
+                                                "the tcgen05 kernel keeps K <= 128 resident)",
+                    "achieved": gemm_tf, "peak": dpk, "unit": "TFLOP/s", "frac": gemm_tf / dpk, "traffic": None,
+                    "peak_source": "FP64 DMMA pipe measured in this run (tools/dmma_bench)" if peaks.get("dmma_tflops") else
+                                   "37.0 TF/s (tools/dmma_bench, round 1)",
+                    "launch_avg_ms": gemm_ms_launch, "launches_in_region": n_gemm,
+                    "algorithmic_flops_per_launch": gemm_flops_launch,
+                    "phase_ms_per_step": {k: v / K for k, v in phases.items()}, "dominant_phase": dom}
         # --- the HBM-bound kernel of the path: fat_kernel_t (label-carrying environment stream)
         fat_bytes = 8.0 * NT * (m + 10 * m + 1) * n_fwd + 8.0 * NT * m * n_bwd
         fat_gbs = fat_bytes / (stt.ms_fat / 1000.0) / 1e9 if stt.ms_fat > 0 else 0.0
         roof_hbm = {"bound": "hbm", "kernel": "fat_kernel_t", "achieved": fat_gbs, "peak": peak, "unit": "GB/s",
                     "frac": fat_gbs / peak, "peak_source": peak_src, "launch_avg_ms": stt.ms_fat / max(1, n_fwd),
-                    "algorithmic_bytes_per_launch": 8.0 * NT * (11 * m + 1)}
-        # --- the serial term: truncated SVD of the 2m x 2m bond matrix (replicated on every rank)
-        svd_info = {"ms_per_step": stt.ms_svd / K, "sweeps": [int(r.svd_sweeps) for r in res_t][:8],
-                    "note": "column sort + 2 Householder QRs + Gram-based block Jacobi (latency bound, ~15 CTAs); "
-                            "largest summed share of the step, see profiles/r01_ncu_summary.md"}
+                    "algorithmic_bytes_per_launch": 8.0 * NT * (11 * m + 1),
+                    "note": "class L/R bonds only" if args.config == 3 else "window incl. class-C bonds: indicative only"}
+        svd_info = {"ms_per_step": stt.ms_svd / K, "sweeps": [int(r.svd_sweeps) for r in res_t][:10],
+                    "note": "column sort + 2 Householder QRs + cluster-resident block Jacobi (latency bound, 16 CTAs), replicated on every rank"}
         line = {"metric": "bond-updates/sec", "value": value, "unit": "bond-updates/sec", "n_gpus": world,
                 "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, world),
                 "images_bonds_per_sec": value * NTg,
+                "value_rightward": n_right / (ms3[1] / 1000.0) if ms3[1] > 0 else None,
+                "value_leftward": n_left / (ms3[2] / 1000.0) if n_left and ms3[2] > 0 else None,
+                "value_sweep_avg": sweep_avg,
                 "e2e": {"value": e2e_value, "unit": "bond-updates/sec", "h2d_bytes_per_step": h2d / K,
                         "d2h_bytes_per_step": d2h / K,
                         "note": "host-resident MPS: W(b),W(b+1) H2D before and D2H after every bond update "
                                 "through the C-ABI; images/environments are resident state (TrainStates)"},
                 "gpu_launches": int(st.launches), "clocks": clocks, "roofline": roof, "roofline_hbm": roof_hbm,
-                "svd": svd_info,
+                "svd": svd_info, "measured_peaks": peaks,
                 "value_cg_reuse_forward": value_reuse,
-                "setup_s": setup_s, "newm": [int(r.newm) for r in res][:8], "newm_min": min(int(r.newm) for r in res),
-                "timed_bonds": [int(timed_bonds[0]), int(timed_bonds[-1])],
+                "setup_s": setup_s, "newm": [int(r.newm) for r in res][:10], "newm_min": min(int(r.newm) for r in res),
+                "timed_bonds": [[int(b), int(ha)] for (b, ha) in sched][:24],
                 "cost_per_image": [r.cost / NTg for r in res][:4]}
         if not args.no_cpu_baseline:
-            base, _ = cpu_baseline(args, steps=1)
-            line["cpu_baseline"] = base
+            if args.config == 3:
+                base, _ = cpu_baseline(args, steps=1)
+                line["cpu_baseline"] = base
+            try:
+                line["cpu_baseline_structured"] = cpu_baseline_structured(args)
+                if args.config == 5:
+                    line["cpu_baseline"] = line["cpu_baseline_structured"]
+            except Exception as e:   # a baseline problem must not lose the GPU measurement
+                line["cpu_baseline_structured"] = {"error": repr(e)}
         print(json.dumps(line))
     h.close()
     if dist is not None:

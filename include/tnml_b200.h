@@ -166,6 +166,10 @@ int tnml_get_env(tnml_handle h, int slot, int* m, int* is_fat, double* data, siz
 #define TNML_UNIQUE_ID_BYTES 128
 int tnml_comm_get_unique_id(uint8_t* id /*[128]*/);
 int tnml_comm_init_rank(tnml_handle h, int nranks, int rank, const uint8_t* id);
+/* Host-side control values that every rank must agree on (the reference is one process: the LAMBDA /
+ * WRITE_WF sentinel files of fixedL.cc:542-559 and the time-seeded RNG of :702-728 are read once there):
+ * the `n` doubles of rank `root` replace vals[] on every rank.  No-op without a communicator. */
+int tnml_comm_broadcast(tnml_handle h, double* vals, int n, int root);
 
 /* Options (name, value).  "cg_reuse_forward" (default 0): 0 = every CG pass recomputes the
  * residual from scratch exactly like fixedL.cc:412-421; 1 = the forward outputs are updated

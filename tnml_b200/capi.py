@@ -55,7 +55,7 @@ SYMBOLS = [
     "tnml_set_site", "tnml_get_site_dims", "tnml_get_site", "tnml_init_envs", "tnml_set_bond",
     "tnml_bond_form", "tnml_bond_dims", "tnml_bond_load", "tnml_bond_store", "tnml_cgrad",
     "tnml_svd_split", "tnml_quadcost", "tnml_shift_env", "tnml_bond_update", "tnml_predict", "tnml_fulltest",
-    "tnml_get_env", "tnml_comm_get_unique_id", "tnml_comm_init_rank", "tnml_set_option", "tnml_get_stats",
+    "tnml_get_env", "tnml_comm_get_unique_id", "tnml_comm_init_rank", "tnml_comm_broadcast", "tnml_set_option", "tnml_get_stats",
     "tnml_set_timing", "tnml_synchronize", "tnml_stream",
 ]
 
@@ -98,6 +98,7 @@ def load_library():
     lib.tnml_get_env.argtypes = [vp, i, ip, ip, vp, C.c_size_t]
     lib.tnml_comm_get_unique_id.argtypes = [vp]
     lib.tnml_comm_init_rank.argtypes = [vp, i, i, vp]
+    lib.tnml_comm_broadcast.argtypes = [vp, dp, i, i]
     lib.tnml_set_option.argtypes = [vp, C.c_char_p, d]
     lib.tnml_get_stats.argtypes = [vp, C.POINTER(Stats), i]
     lib.tnml_set_timing.argtypes = [vp, i]
@@ -248,6 +249,11 @@ class Handle:
     def comm_init_rank(self, nranks, rank, uid: bytes):
         buf = (C.c_uint8 * UNIQUE_ID_BYTES).from_buffer_copy(uid)
         self._ck(self.lib.tnml_comm_init_rank(self._h, nranks, rank, buf))
+
+    def comm_broadcast(self, vals, root=0):
+        buf = (C.c_double * len(vals))(*[float(v) for v in vals])
+        self._ck(self.lib.tnml_comm_broadcast(self._h, buf, len(vals), root))
+        return list(buf)
 
     def set_option(self, name: str, value: float):
         self._ck(self.lib.tnml_set_option(self._h, name.encode(), float(value)))

@@ -143,7 +143,9 @@ struct tnml_handle_s {
   double* stats_partial = nullptr;
   unsigned* ticket = nullptr;   // last-CTA ticket of the statistics reduction inside fat_kernel
   int nfat_blocks = 0;
-  double* dscal = nullptr;  // [32] device scalars
+  double* dscal = nullptr;  // [64] device scalars
+  double* cgs = nullptr;    // [32] device state of the CG recurrence (see cgrad_enqueue)
+  int last_svd_sweeps = 0;
   double* dot_scratch = nullptr;
   double* hpin = nullptr;  // pinned host [64]
   SvdWork svd;
@@ -587,11 +589,10 @@ int fetch(tnml_handle h, const double* dsrc, int n, double* hdst) {
   return 0;
 }
 
-// gradient evaluation at X: G (+16 stats tail, all-reduced), host stats out
-// After the all-reduce: G -= lambda*X (fixedL.cc:386,422), |G|^2 into slot 12 of the 16-double tail,
-// then ONE read-back for the cost statistics and the residual norm (each read-back drains the
-// stream: ~15 us of idle GPU, 17 of them per bond update before they were merged).
-int finish_grad(tnml_handle h, const double* X, double lambda, double* hstats) {
+// gradient evaluation at X: G (+16 stats tail, all-reduced).  After the all-reduce: G -= lambda*X
+// (fixedL.cc:386,422) and |G|^2 into slot 12 of the 16-double tail.  Nothing is read back: the CG
+// scalars (|r|^2, beta, step size, costs per pass, convergence flag) live in h->cgs on the device.
+int finish_grad(tnml_handle h, const double* X, double lambda) {
   const long n = h->g.size();
   if (lambda != 0.0) {
     axpby(h->st, n, -lambda, X, 1.0, h->G.p);
@@ -601,26 +602,23 @@ int finish_grad(tnml_handle h, const double* X, double lambda, double* hstats) {
   dot(h->st, n, h->G.p, h->G.p, h->dot_scratch, h->G.p + n + 12);
   CKL();
   h->stats.launches += 2;
-  // |r|^2 also stays on the device (dscal[20]) for the next step size a = |r|^2 / pAp
-  CK(cudaMemcpyAsync(h->dscal + 20, h->G.p + n + 12, sizeof(double), cudaMemcpyDeviceToDevice, h->st));
-  TRY(fetch(h, h->G.p + n, 16, hstats));
   return 0;
 }
 
-int grad_eval(tnml_handle h, const double* X, double lambda, double* hstats) {
+int grad_eval(tnml_handle h, const double* X, double lambda) {
   const long n = h->g.size();
   TRY(ensure(h, h->G, (size_t)n + 16));
   TRY(forward(h, X, FAT_GRAD, h->dscal));
   TRY(backward(h));
   CK(cudaMemcpyAsync(h->G.p + n, h->dscal, 16 * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
   TRY(allreduce(h, h->G.p, (size_t)n + 16));
-  return finish_grad(h, X, lambda, hstats);
+  return finish_grad(h, X, lambda);
 }
 
 // cg_reuse_forward: the forward outputs are linear in the bond tensor, P(B + a p) = P(B) + a P(p),
 // and P(p) was just computed for pAp -- so the next residual needs only the backward half:
 // dP = delta - P, cost statistics, Z (one pass over the fat environment) and the krgram contraction.
-int grad_from_P(tnml_handle h, const double* X, double lambda, double* hstats) {
+int grad_from_P(tnml_handle h, const double* X, double lambda) {
   const int b = h->currb;
   const BondGeom& g = h->g;
   EnvRef le, re;
@@ -649,7 +647,7 @@ int grad_from_P(tnml_handle h, const double* X, double lambda, double* hstats) {
   TRY(backward(h));
   CK(cudaMemcpyAsync(h->G.p + n, h->dscal, 16 * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
   TRY(allreduce(h, h->G.p, (size_t)n + 16));
-  return finish_grad(h, X, lambda, hstats);
+  return finish_grad(h, X, lambda);
 }
 
 int ddot(tnml_handle h, long n, const double* x, const double* y, double* out) {
@@ -800,6 +798,7 @@ int tnml_create(int device, int flags, tnml_handle* out) {
   if (cudaMalloc(&h->stats_partial, (size_t)h->nfat_blocks * 16 * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->ticket, 64) != cudaSuccess || cudaMemset(h->ticket, 0, 64) != cudaSuccess ||
       cudaMalloc(&h->dscal, 64 * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&h->cgs, 32 * sizeof(double)) != cudaSuccess || cudaMemset(h->cgs, 0, 32 * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->dot_scratch, 1024 * sizeof(double)) != cudaSuccess ||
       cudaMallocHost(&h->hpin, 64 * sizeof(double)) != cudaSuccess) {
     delete h;
@@ -828,7 +827,7 @@ int tnml_destroy(tnml_handle h) {
   for (DBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   void* ptrs[] = {h->feat, h->labels, h->ones, h->P, h->PV, h->pred, h->stats_partial, h->ticket, h->dscal, h->dot_scratch,
-                  h->oz_A8, h->oz_ea, h->oz_B8, h->oz_eb,
+                  h->oz_A8, h->oz_ea, h->oz_B8, h->oz_eb, h->cgs,
                   h->svd.X, h->svd.J, h->svd.sig2, h->svd.perm, h->svd.info, h->svd.flags,
                   h->svd.M, h->svd.tau, h->svd.ready, h->svd.Y, h->svd.M2, h->svd.tau2, h->svd.Y2, h->svd.perm0, h->svd.sweepmax};
   for (void* p : ptrs)
@@ -1032,21 +1031,23 @@ int tnml_bond_store(tnml_handle h, double* B, size_t capacity_elems) {
   return TNML_OK;
 }
 
-int tnml_cgrad(tnml_handle h, int Npass, double lambda, double cconv, double* cost_per_pass,
-               double* rnorm_per_pass, int* npass_done) {
-  if (!h || !h->bond_valid) return h ? fail(h, TNML_ERR_INVALID, "no bond tensor formed") : TNML_ERR_INVALID;
-  if (Npass < 1) return fail(h, TNML_ERR_INVALID, "Npass must be >= 1");
-  CK(cudaSetDevice(h->device));
+// cgrad (fixedL.cc:349-445), enqueue half: every kernel of the Npass passes is queued without a
+// single host read-back.  The scalars of the recurrence stay in h->cgs (device):
+//   [0] |r|^2  [1] beta  [2] converged flag  [3] passes recorded  [4] step a  [8..15] C/NT per pass  [16..23] |r| per pass
+// `|r| < cconv` (fixedL.cc:432-436) cannot break a queue that is already enqueued; instead the flag
+// freezes the state: every later step size is 0 and no later cost is recorded, so B, the costs and
+// the pass count are exactly what the reference's `break` leaves behind (the remaining passes are
+// wasted work in that -- in practice never taken -- case).
+static int cgrad_enqueue(tnml_handle h, int Npass, double lambda, double cconv) {
   const long n = h->g.size();
-  TRY(ensure(h, h->r, (size_t)n));
   TRY(ensure(h, h->p, (size_t)n));
-  double hs[16];
-  int nd = 0;
-  // r = sum_n (delta - B v_n) v_n - lambda B     (fixedL.cc:373-386)
-  TRY(grad_eval(h, h->B.p, lambda, hs));              // G = sum_n dP_n v_n - lambda B, hs[12] = |G|^2
-  CK(cudaMemcpyAsync(h->r.p, h->G.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
-  CK(cudaMemcpyAsync(h->p.p, h->r.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->st));  // p = r (388)
-  double rr = hs[12];
+  double* cgs = h->cgs;
+  // r = sum_n (delta - B v_n) v_n - lambda B     (fixedL.cc:373-386); p = r (388)
+  TRY(grad_eval(h, h->B.p, lambda));
+  cg_begin(h->st, h->G.p + n, cgs);
+  CKL();
+  CK(cudaMemcpyAsync(h->p.p, h->G.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  h->stats.launches += 1;
   for (int pass = 1; pass <= Npass; ++pass) {
     // pAp = sum_n |p v_n|^2 + lambda |p|^2          (393-403)
     TRY(forward(h, h->p.p, FAT_PAP, h->dscal, h->cg_reuse_forward ? h->PV : nullptr));
@@ -1056,44 +1057,55 @@ int tnml_cgrad(tnml_handle h, int Npass, double lambda, double cconv, double* co
       CKL();
       h->stats.launches += 2;
     }
-    // a = |r|^2 / pAp (405) and B += a p (406) on the device: no read-back between the pAp pass and
-    // the next gradient (|r|^2 is in dscal[20] since the last gradient, pAp in dscal[11])
-    cg_step(h->st, h->dscal + 20, h->dscal + 11, lambda, h->dscal + 21, h->dscal + 22);
+    // a = |r|^2 / pAp (405) and B += a p (406)
+    cg_step(h->st, cgs, h->dscal + 11, lambda, h->dscal + 21);
     CKL();
-    axpby_dev(h->st, n, h->dscal + 22, h->p.p, 1.0, h->B.p);
+    axpby_dev(h->st, n, cgs + 4, h->p.p, 1.0, h->B.p);
     CKL();
     h->stats.launches += 2;
     if (pass == Npass) break;                         // 409
     if (h->cg_reuse_forward) {
-      axpby_dev(h->st, (long)h->NT * NL, h->dscal + 22, h->PV, 1.0, h->P);   // P(B + a p) = P(B) + a P(p)
+      axpby_dev(h->st, (long)h->NT * NL, cgs + 4, h->PV, 1.0, h->P);   // P(B + a p) = P(B) + a P(p)
       CKL();
       h->stats.launches += 1;
-      TRY(grad_from_P(h, h->B.p, lambda, hs));
+      TRY(grad_from_P(h, h->B.p, lambda));
     } else {
-      TRY(grad_eval(h, h->B.p, lambda, hs));          // 412-422 (incl. nr -= lambda*B)
+      TRY(grad_eval(h, h->B.p, lambda));              // 412-422 (incl. nr -= lambda*B)
     }
-    const double nrr = hs[12];
-    const double beta = nrr / rr;                     // 423
-    CK(cudaMemcpyAsync(h->r.p, h->G.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->st));  // 424
-    rr = nrr;
-    double C = 0.0;
-    for (int l = 0; l < NL; ++l) C += hs[l];          // 427
     if (lambda != 0.0) {
-      double bb = 0.0;
-      TRY(ddot(h, n, h->B.p, h->B.p, &bb));
-      C += lambda * bb;                               // 428
+      dot(h->st, n, h->B.p, h->B.p, h->dot_scratch, h->dscal + 23);   // 428
+      CKL();
+      h->stats.launches += 2;
     }
-    if (nd < 8) {
-      if (cost_per_pass) cost_per_pass[nd] = C / (double)h->NTg;  // 429
-      if (rnorm_per_pass) rnorm_per_pass[nd] = std::sqrt(rr);
-    }
-    ++nd;
-    if (std::sqrt(rr) < cconv) break;                 // 432-436
-    axpby(h->st, n, 1.0, h->r.p, beta, h->p.p);       // p = r + beta p (442)
+    // beta = (|nr|/|r|)^2 (423), r = nr (424), C (427-428), cost line (429), |r| < cconv (432)
+    cg_after_grad(h->st, h->G.p + n, cgs, lambda, h->dscal + 23, (double)h->NTg, cconv);
     CKL();
-    h->stats.launches += 1;
+    xpby_dev(h->st, n, h->G.p, cgs + 1, h->p.p);      // p = r + beta p (442)
+    CKL();
+    h->stats.launches += 2;
+  }
+  return 0;
+}
+
+static void cgrad_collect(const double* hc, double* cost_per_pass, double* rnorm_per_pass, int* npass_done) {
+  int nd = (int)hc[3];
+  if (nd > 8) nd = 8;
+  for (int i = 0; i < nd; ++i) {
+    if (cost_per_pass) cost_per_pass[i] = hc[8 + i];
+    if (rnorm_per_pass) rnorm_per_pass[i] = hc[16 + i];
   }
   if (npass_done) *npass_done = nd;
+}
+
+int tnml_cgrad(tnml_handle h, int Npass, double lambda, double cconv, double* cost_per_pass,
+               double* rnorm_per_pass, int* npass_done) {
+  if (!h || !h->bond_valid) return h ? fail(h, TNML_ERR_INVALID, "no bond tensor formed") : TNML_ERR_INVALID;
+  if (Npass < 1) return fail(h, TNML_ERR_INVALID, "Npass must be >= 1");
+  CK(cudaSetDevice(h->device));
+  TRY(cgrad_enqueue(h, Npass, lambda, cconv));
+  double hc[24];
+  TRY(fetch(h, h->cgs, 24, hc));                      // the one read-back of the whole CG
+  cgrad_collect(hc, cost_per_pass, rnorm_per_pass, npass_done);
   return TNML_OK;
 }
 
@@ -1125,7 +1137,7 @@ int tnml_svd_split(tnml_handle h, int dir, double cutoff, int maxm, int minm, in
   h->W[b].mr = m;
   h->W[b + 1].ml = m;
   h->stats.alg_flops += 4.0 * std::max(nA, nB) * (double)std::min(nA, nB) * std::min(nA, nB);
-  h->hpin[32] = (double)sweeps;
+  h->last_svd_sweeps = sweeps;
   if (newm) *newm = m;
   if (truncerr) *truncerr = terr;
   return TNML_OK;
@@ -1197,11 +1209,13 @@ int tnml_bond_update(tnml_handle h, int b, int ha, const tnml_bond_params* p, tn
   TRY(tnml_set_bond(h, b));                                            // 488
   TRY(tnml_bond_form(h));                                              // 493-498
   res.origm = h->W[b].mr;
-  TRY(tnml_cgrad(h, p->Npass, p->lambda, p->cconv, res.cg_cost, res.cg_rnorm, &res.npass_done));  // 504
+  if (!h->bond_valid) return fail(h, TNML_ERR_INVALID, "no bond tensor formed");
+  if (p->Npass < 1) return fail(h, TNML_ERR_INVALID, "Npass must be >= 1");
+  TRY(cgrad_enqueue(h, p->Npass, p->lambda, p->cconv));                   // 504 (scalars read back below)
   const long n = h->g.size();
   TRY(tnml_svd_split(h, ha == 1 ? TNML_FROMLEFT : TNML_FROMRIGHT, p->cutoff, p->maxm, p->minm, p->do_rel_cutoff,
                      &res.newm, &res.truncerr));                        // 519-521
-  res.svd_sweeps = (int)h->hpin[32];
+  res.svd_sweeps = h->last_svd_sweeps;
   // quadcost(newB) (527-532, newB in T), |B| and |B - newB| (528-530) and shiftE (540) are all
   // enqueued before the single read-back of their scalars, so the GPU stays busy while the host waits
   TRY(quadcost_enqueue(h, 1, p->lambda));
@@ -1214,9 +1228,12 @@ int tnml_bond_update(tnml_handle h, int b, int ha, const tnml_bond_params* p, tn
   h->stats.launches += 5;
   h->bond_valid = false;
   TRY(tnml_shift_env(h, b, ha == 1 ? TNML_FROMLEFT : TNML_FROMRIGHT));  // 540
-  double hs[19];
-  TRY(fetch(h, h->dscal, 19, hs));
+  double hs[19 + 24];
+  CK(cudaMemcpyAsync(h->hpin + 19, h->cgs, 24 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  TRY(fetch(h, h->dscal, 19, hs));                                       // one synchronisation for both
+  memcpy(hs + 19, h->hpin + 19, 24 * sizeof(double));
   quadcost_collect(hs, p->lambda, &res.cost, res.cost_label, &res.ncorrect);
+  cgrad_collect(hs + 19, res.cg_cost, res.cg_rnorm, &res.npass_done);
   res.normB = std::sqrt(hs[16]);
   res.dB = std::sqrt(hs[17]);
   if (out) *out = res;
@@ -1285,6 +1302,19 @@ int tnml_comm_init_rank(tnml_handle h, int nranks, int rank, const uint8_t* id) 
   h->comm = comm;
   h->nranks = nranks;
   h->rank = rank;
+  return TNML_OK;
+}
+
+int tnml_comm_broadcast(tnml_handle h, double* vals, int n, int root) {
+  if (!h || !vals || n < 1 || n > 16) return h ? fail(h, TNML_ERR_INVALID, "bad broadcast args (1 <= n <= 16)") : TNML_ERR_INVALID;
+  if (!h->comm) return TNML_OK;
+  if (root < 0 || root >= h->nranks) return fail(h, TNML_ERR_INVALID, "bad root %d", root);
+  CK(cudaSetDevice(h->device));
+  // sum-all-reduce with zeros from every rank but the root (the library's only collective)
+  for (int i = 0; i < n; ++i) h->hpin[i] = (h->rank == root) ? vals[i] : 0.0;
+  CK(cudaMemcpyAsync(h->dscal + 40, h->hpin, n * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  TRY(allreduce(h, h->dscal + 40, (size_t)n));
+  TRY(fetch(h, h->dscal + 40, n, vals));
   return TNML_OK;
 }
 

@@ -1325,16 +1325,65 @@ void axpby_dev(cudaStream_t st, long n, const double* a_ptr, const double* x, do
   if (n <= 0) return;
   axpby_dev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, a_ptr, x, b, y);
 }
-__global__ void cg_step_kernel(const double* __restrict__ rr, const double* __restrict__ pAp, double lambda,
-                               const double* __restrict__ pp, double* __restrict__ a_out) {
+// ---- device-side scalars of the CG recurrence (fixedL.cc:388-443): cgs = [0] |r|^2, [1] beta, [2] converged,
+// [3] passes recorded, [4] step a, [8..15] C/NT per pass, [16..23] |r| per pass; `tail` = the 16 statistics behind G
+// (cost per label in 0..9, |G|^2 in 12)
+__global__ void cg_begin_kernel(const double* __restrict__ tail, double* __restrict__ cgs) {
+  if (threadIdx.x == 0) {
+    cgs[0] = tail[12];
+    cgs[1] = 0.0;
+    cgs[2] = 0.0;
+    cgs[3] = 0.0;
+    cgs[4] = 0.0;
+  }
+}
+void cg_begin(cudaStream_t st, const double* tail, double* cgs) { cg_begin_kernel<<<1, 32, 0, st>>>(tail, cgs); }
+
+__global__ void cg_step_kernel(double* __restrict__ cgs, const double* __restrict__ pAp, double lambda,
+                               const double* __restrict__ pp) {
   if (threadIdx.x == 0) {
     double d = pAp[0];
     if (lambda != 0.0) d += lambda * pp[0];
-    a_out[0] = rr[0] / d;
+    cgs[4] = (cgs[2] != 0.0) ? 0.0 : cgs[0] / d;      // a = |r|^2 / pAp (405); frozen once |r| < cconv
   }
 }
-void cg_step(cudaStream_t st, const double* rr, const double* pAp, double lambda, const double* pp, double* a_out) {
-  cg_step_kernel<<<1, 32, 0, st>>>(rr, pAp, lambda, pp, a_out);
+void cg_step(cudaStream_t st, double* cgs, const double* pAp, double lambda, const double* pp) {
+  cg_step_kernel<<<1, 32, 0, st>>>(cgs, pAp, lambda, pp);
+}
+
+__global__ void cg_after_grad_kernel(const double* __restrict__ tail, double* __restrict__ cgs, double lambda,
+                                     const double* __restrict__ bb, double NTg, double cconv) {
+  if (threadIdx.x == 0 && cgs[2] == 0.0) {
+    const double nrr = tail[12];
+    cgs[1] = nrr / cgs[0];                            // beta = (|nr|/|r|)^2 (423)
+    cgs[0] = nrr;                                     // r = nr (424)
+    double C = 0.0;
+    for (int l = 0; l < NL; ++l) C += tail[l];        // 427
+    if (lambda != 0.0) C += lambda * bb[0];           // 428
+    const int nd = (int)cgs[3];
+    if (nd < 8) {
+      cgs[8 + nd] = C / NTg;                          // 429
+      cgs[16 + nd] = sqrt(nrr);
+    }
+    cgs[3] = (double)(nd + 1);
+    if (sqrt(nrr) < cconv) cgs[2] = 1.0;              // 432-436: no further update of p or B
+  }
+}
+void cg_after_grad(cudaStream_t st, const double* tail, double* cgs, double lambda, const double* bb, double NTg,
+                   double cconv) {
+  cg_after_grad_kernel<<<1, 32, 0, st>>>(tail, cgs, lambda, bb, NTg, cconv);
+}
+
+// y = x + (*b) * y   (p = r + beta p, fixedL.cc:442)
+__global__ void xpby_dev_kernel(long n, const double* __restrict__ x, const double* __restrict__ b_ptr,
+                                double* __restrict__ y) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const double b = *b_ptr;
+  if (i < n) y[i] = fma(b, y[i], x[i]);
+}
+void xpby_dev(cudaStream_t st, long n, const double* x, const double* b_ptr, double* y) {
+  if (n <= 0) return;
+  xpby_dev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, x, b_ptr, y);
 }
 
 constexpr int DOT_BLOCKS = 128;

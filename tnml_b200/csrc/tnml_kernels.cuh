@@ -104,9 +104,15 @@ void permute_site(cudaStream_t st, const double* W, int ma, int mb, int nl, int 
 void fill(cudaStream_t st, double* x, long n, double v);
 // y = a*x + b*y
 void axpby(cudaStream_t st, long n, double a, const double* x, double b, double* y);
-// y = (*a_ptr)*x + b*y ; *a_out = *rr / (*pAp + lambda * *pp)   (CG step of fixedL.cc:405-406 on the device)
+// y = (*a_ptr)*x + b*y with the scalar read from device memory
 void axpby_dev(cudaStream_t st, long n, const double* a_ptr, const double* x, double b, double* y);
-void cg_step(cudaStream_t st, const double* rr, const double* pAp, double lambda, const double* pp, double* a_out);
+// y = x + (*b_ptr)*y
+void xpby_dev(cudaStream_t st, long n, const double* x, const double* b_ptr, double* y);
+// scalars of the CG recurrence on the device (fixedL.cc:388-443); layout of cgs[32] in tnml_kernels.cu
+void cg_begin(cudaStream_t st, const double* tail, double* cgs);
+void cg_step(cudaStream_t st, double* cgs, const double* pAp, double lambda, const double* pp);
+void cg_after_grad(cudaStream_t st, const double* tail, double* cgs, double lambda, const double* bb, double NTg,
+                   double cconv);
 // out[0] = sum x*y (deterministic two-stage)
 void dot(cudaStream_t st, long n, const double* x, const double* y, double* scratch, double* out);
 

@@ -132,6 +132,52 @@ def synthetic_digits(NT, L=14, seed=20260925, first=0, nproto=10):
     return out, labels
 
 
+def _splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    x = ((x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    x = ((x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    return x ^ (x >> np.uint64(31))
+
+
+def synthetic_pixels(NT, npix, seed=20260925, first=0):
+    """BASELINE config 5 recipe: counter-based hash RNG splitmix64(seed, image, pixel) ->
+    zero with probability 0.81, else uniform{1..255} (MNIST sparsity: 19.1 % non-zero); label = image
+    mod 10.  Vectorised, any shard [first, first+NT) of the global set is reproducible.
+    Returns (pixels / 255 as float64 [NT, npix], labels int32)."""
+    with np.errstate(over="ignore"):
+        img = (np.arange(NT, dtype=np.uint64) + np.uint64(first))[:, None]
+        pixi = np.arange(npix, dtype=np.uint64)[None, :]
+        h = _splitmix64(_splitmix64(np.uint64(seed) + img * np.uint64(1000003)) + pixi)
+        u = (h >> np.uint64(11)).astype(np.float64) / 9007199254740992.0
+        v = _splitmix64(h)
+        val = (v % np.uint64(255)).astype(np.float64) + 1.0
+    out = np.where(u < 0.81, 0.0, val) / 255.0
+    labels = ((np.arange(NT, dtype=np.int64) + first) % NL).astype(np.int32)
+    return out, labels
+
+
+def window_mps(N, d=2, m=300, seed=5, jc=None):
+    """Short chain with the SAME link dimension m on every interior bond (config-5 window, SURVEY 8d:
+    the kernels at m_l = m_r = maxm are measured on a few sites instead of a 196-site chain whose
+    environments would not fit): i.i.d. N(0, 1/(m_a d)) site tensors with a near-identity s=0 slice,
+    label index on site N//2, centre tensors normalised."""
+    jc = N // 2 if jc is None else jc
+    rng = np.random.default_rng(seed)
+    dims = [1] + [m] * (N - 1) + [1]
+    W = [None] * (N + 1)
+    for j in range(1, N + 1):
+        ml, mr = dims[j - 1], dims[j]
+        shape = (ml, d, mr, NL) if j == jc else (ml, d, mr)
+        A = rng.standard_normal(shape) / np.sqrt(ml * d)
+        if j == jc:
+            A[:, 0, :, :] += np.eye(ml, mr)[:, :, None]
+        else:
+            A[:, 0, :] += np.eye(ml, mr)
+        W[j] = A / np.linalg.norm(A) * np.sqrt(min(ml, mr))
+    W[jc] = W[jc] / np.linalg.norm(W[jc])
+    return W
+
+
 def random_mps(N, d=2, m=10, seed=1, noise=0.3, jc=None):
     """Deterministic start MPS (replaces the time-seeded init of
     fixedL.cc:702-728): near-identity s=0 slices so environments stay

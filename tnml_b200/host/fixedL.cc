@@ -268,21 +268,36 @@ void mldmrg(MPS& W, TrainStates& ts, Sweeps const& sweeps, Args args) {
       // Update E's (MPS environment tensors)
       ts.shiftE(W, b, ha == 1 ? Fromleft : Fromright);
 
-      if (fileExists("WRITE_WF")) {
+      // Sentinel files (fixedL.cc:542-559).  The reference is ONE process; here rank 0 alone looks at
+      // (and removes) the files and its findings are broadcast, so that every rank writes W at the
+      // same bond and continues with the same lambda (r = G - lambda*B and the replicated SVD must
+      // stay bit-identical across ranks).
+      double ctl[3] = {0., 0., 0.};   // WRITE_WF seen, LAMBDA seen, new lambda
+      if (ts.rank_ == 0) {
+        if (fileExists("WRITE_WF")) {
+          std::remove("WRITE_WF");
+          ctl[0] = 1.;
+        }
+        if (fileExists("LAMBDA")) {
+          std::ifstream lf("LAMBDA");
+          Real lambda = 0.;
+          lf >> lambda;
+          lf.close();
+          std::remove("LAMBDA");
+          ctl[1] = 1.;
+          ctl[2] = lambda;
+        }
+      }
+      if (ts.world_ > 1) TN(tnml_comm_broadcast(h_, ctl, 3, 0));
+      if (ctl[0] != 0.) {
         println("File WRITE_WF found");
-        std::remove("WRITE_WF");
         println("Writing W to disk");
         for (int j = 1; j <= N; ++j) ts.download(W, j);
         if (ts.rank_ == 0) writeToFile("W", W);
       }
-      if (fileExists("LAMBDA")) {
-        std::ifstream lf("LAMBDA");
-        Real lambda = 0.;
-        lf >> lambda;
-        lf.close();
-        args.add("lambda", lambda);
-        std::remove("LAMBDA");
-        println("new lambda = ", lambda);
+      if (ctl[1] != 0.) {
+        args.add("lambda", ctl[2]);
+        println("new lambda = ", ctl[2]);
       }
       if (pause_step) {
         println("(Paused, press enter to continue)");
@@ -434,6 +449,8 @@ int main(int argc, const char* argv[]) {
     int rank = std::getenv("TNML_RANK") ? atoi(std::getenv("TNML_RANK")) : 0;
     int world = std::getenv("TNML_WORLD_SIZE") ? atoi(std::getenv("TNML_WORLD_SIZE")) : 1;
     if (device < 0) device = rank;
+    // every rank builds the same initial W from the same seed; a time seed would give each rank its own
+    if (world > 1 && seed < 0) Error("seed < 0 (time-seeded initial W) needs an explicit seed when TNML_WORLD_SIZE > 1");
 
     auto train = mllib::readMNIST(datadir, mllib::Train, Ntrain);
     if (imglen != 28) {

@@ -153,6 +153,28 @@ int main() {
       }
     }
   }
+  // sustained int8 tensor peak at whatever clock the power cap allows (wall clock, CUDA events)
+  {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int big = 16384;
+    umma_bench_kernel<<<148, 288, sh>>>(256, 0, big, d, 0, 0, 0, sink);
+    cudaEventRecord(e0);
+    umma_bench_kernel<<<148, 288, sh>>>(256, 0, big, d, 0, 0, 0, sink);
+    cudaEventRecord(e1);
+    cudaDeviceSynchronize();
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    std::vector<long long> h(148);
+    cudaMemcpy(h.data(), d, 148 * sizeof(long long), cudaMemcpyDeviceToHost);
+    double cyc = 0;
+    for (auto v : h) cyc += (double)v;
+    cyc /= 148;
+    const double ops = 148.0 * 2.0 * big * 2.0 * 128.0 * 256.0 * 32.0;   // 2 passes inside the kernel
+    printf("INT8_PEAK_TOPS %.1f  (tcgen05.mma kind::i8 M=128 N=256 K=32 back to back on 148 SMs, %.3f ms, SM clock %.0f MHz under load)\n",
+           ops / (ms * 1e-3) / 1e12, ms, cyc / (ms * 0.5 * 1e-3) / 1e6);
+  }
   cudaFree(d);
   return 0;
 }
