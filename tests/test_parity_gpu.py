@@ -598,3 +598,46 @@ def test_fulltest_matches_oracle(capi):
     assert abs(ncor - ncor_o) <= 2 and np.sum(pred != pred_o) <= 3
     assert lines[0].startswith(f"{ncor}/300 correct") and lines[-1] == "Total # test images = 300"
     assert ncor > 60     # learned something (chance = 30)
+
+
+def test_svd_rank_deficient_isometry(capi):
+    """ITensor's svd returns orthonormal U columns also for zero singular values; Minm can force such
+    vectors to be kept (real MNIST border sites have phi = [1, 0] for every image, so the bond matrix
+    is rank deficient there).  The device SVD completes the null-space columns: W(c) is an isometry,
+    m / truncerr / U S V still match the oracle.  Direct Jacobi path (16 columns) and QR path (40)."""
+    rng = np.random.default_rng(11)
+    for m0, N, jc, cases in ((8, 12, 6, [(4, 1), (4, 2), (6, 1), (5, 2), (8, 1)]), (20, 16, 8, [(6, 1), (10, 2)])):
+        feat, labels, W = make_problem(N=N, NT=64, m0=m0)
+        for b, ha in cases:
+            h = _gpu_state(capi, feat, labels, W)
+            for bb in range(1, b):
+                h.set_bond(bb)
+                h.shift_env(bb, capi.FROMLEFT)
+            h.set_bond(b)
+            B0 = O.form_bond(W[b], W[b + 1])
+            # rank-3 bond matrix whose odd rows and odd columns vanish exactly (like s = 1 slices on
+            # border pixels), folded back into the tensor layout through bond_matrix of an index probe
+            Im, _ = O.bond_matrix(np.arange(B0.size, dtype=np.float64).reshape(B0.shape), b, ha, jc)
+            M = rng.standard_normal((Im.shape[0], 3)) @ rng.standard_normal((3, Im.shape[1]))
+            M[1::2, :] = 0.0
+            M[:, 1::2] = 0.0
+            B = np.zeros(B0.size)
+            B[Im.astype(np.int64).reshape(-1)] = M.reshape(-1)
+            B = B.reshape(B0.shape)
+            assert np.array_equal(O.bond_matrix(B, b, ha, jc)[0], M)
+            keep = 6
+            Wb, Wb1, m, te = O.svd_split(B, b, ha, jc, 8, keep, 1e-10)
+            assert m == keep                                    # Minm forces 3 zero-sigma vectors in
+            h.bond_load(B)
+            gm, gte = h.svd_split(capi.FROMLEFT if ha == 1 else capi.FROMRIGHT, 1e-10, 8, keep)
+            assert gm == m and abs(gte - te) <= 1e-9 * max(te, 1e-300) + 1e-24 * np.linalg.norm(B) ** 2
+            gWb, gWb1 = h.get_site(b), h.get_site(b + 1)
+            assert rel(O.form_bond(gWb, gWb1), B) < 1e-11, (m0, b, ha)
+            iso = gWb if ha == 1 else gWb1
+            if ha == 1:
+                Ug = (np.transpose(iso, (0, 1, 3, 2)) if iso.ndim == 4 else iso).reshape(-1, m)
+                assert np.abs(Ug.T @ Ug - np.eye(m)).max() < 1e-12, (m0, b, ha)
+            else:
+                Vg = iso.reshape(m, -1)
+                assert np.abs(Vg @ Vg.T - np.eye(m)).max() < 1e-12, (m0, b, ha)
+            h.close()

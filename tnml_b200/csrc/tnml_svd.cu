@@ -1032,6 +1032,117 @@ svd_finalize_kernel(const double* __restrict__ X, int nb, int ns, double* __rest
     }
     info[1] = (double)m;
     info[2] = terr / scale;
+    int nz = 0;                                   // kept vectors whose singular value is exactly zero
+    for (int k = 0; k < m; ++k) nz += (sig2[perm[k]] > 0.0) ? 0 : 1;
+    info[7] = (double)nz;
+  }
+}
+
+// ITensor's svd returns orthonormal U columns also for zero singular values (Minm can force them
+// to be kept: real MNIST border sites have phi = [1, 0] for every image, so bond matrices there are
+// rank deficient).  The scatter kernels leave such columns zero; this pass completes them: for each
+// zero column, the unit vector e_r with the smallest weight in the span of the other columns,
+// projected out of that span (one projection from the row of U, one re-orthogonalisation).
+// iso(r, k) = W[(r / nl) * (m * nl) + k * nl + (r % nl)]  (dir 1)  |  W[k * nrows + r]  (dir 2).  One CTA.
+__global__ void __launch_bounds__(1024)
+svd_complete_iso_kernel(double* __restrict__ W, int nrows, int m, int nl, int dir1) {
+  extern __shared__ double csm[];
+  double* v = csm;                 // [nrows]
+  double* coef = csm + nrows;      // [m]
+  double* red = coef + m;          // [32]
+  __shared__ int s_row, s_col;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  auto at = [&](int r, int k) -> double& {
+    return dir1 ? W[(long)(r / nl) * ((long)m * nl) + (long)k * nl + (r % nl)] : W[(long)k * nrows + r];
+  };
+  for (int guard = 0; guard < m; ++guard) {
+    // first zero column (column norms by warps)
+    if (tid == 0) s_col = m;
+    __syncthreads();
+    for (int k = warp; k < m; k += nw) {
+      double a = 0.0;
+      for (int r = lane; r < nrows; r += 32) a = fma(at(r, k), at(r, k), a);
+      a = wsum(a);
+      if (lane == 0 && a < 0.25) atomicMin(&s_col, k);
+    }
+    __syncthreads();
+    const int c = s_col;
+    if (c >= m) return;
+    // row with the smallest weight sum_k U[r][k]^2
+    double best = 1e300;
+    int brow = 0;
+    for (int r = tid; r < nrows; r += blockDim.x) {
+      double a = 0.0;
+      for (int k = 0; k < m; ++k) a = fma(at(r, k), at(r, k), a);
+      if (a < best) {
+        best = a;
+        brow = r;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int orow = __shfl_xor_sync(0xffffffffu, brow, o);
+      if (ob < best || (ob == best && orow < brow)) {
+        best = ob;
+        brow = orow;
+      }
+    }
+    if (lane == 0) {
+      red[warp] = best;
+      reinterpret_cast<int*>(red + 32)[warp] = brow;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double b = red[0];
+      int br = reinterpret_cast<int*>(red + 32)[0];
+      for (int w2 = 1; w2 < nw; ++w2) {
+        const double ob = red[w2];
+        const int orow = reinterpret_cast<int*>(red + 32)[w2];
+        if (ob < b || (ob == b && orow < br)) {
+          b = ob;
+          br = orow;
+        }
+      }
+      s_row = br;
+    }
+    __syncthreads();
+    const int e = s_row;
+    for (int k = tid; k < m; k += blockDim.x) coef[k] = at(e, k);
+    __syncthreads();
+    for (int r = tid; r < nrows; r += blockDim.x) {
+      double a = (r == e) ? 1.0 : 0.0;
+      for (int k = 0; k < m; ++k) a = fma(-at(r, k), coef[k], a);
+      v[r] = a;
+    }
+    __syncthreads();
+    // re-orthogonalise against every other column, then normalise
+    for (int k = warp; k < m; k += nw) {
+      double d = 0.0;
+      for (int r = lane; r < nrows; r += 32) d = fma(at(r, k), v[r], d);
+      d = wsum(d);
+      if (lane == 0) coef[k] = (k == c) ? 0.0 : d;
+    }
+    __syncthreads();
+    double nn = 0.0;
+    for (int r = tid; r < nrows; r += blockDim.x) {
+      double a = v[r];
+      for (int k = 0; k < m; ++k) a = fma(-at(r, k), coef[k], a);
+      v[r] = a;
+      nn = fma(a, a, nn);
+    }
+    nn = wsum(nn);
+    if (lane == 0) red[warp] = nn;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w2 = 0; w2 < nw; ++w2) t += red[w2];
+      red[0] = 1.0 / sqrt(t);
+    }
+    __syncthreads();
+    const double inv = red[0];
+    for (int r = tid; r < nrows; r += blockDim.x) at(r, c) = v[r] * inv;
+    __threadfence_block();
+    __syncthreads();
   }
 }
 
@@ -1174,7 +1285,7 @@ __global__ void __launch_bounds__(256, 1)
 qr_dataflow_smem_kernel(double* __restrict__ X, int nb, int ns, double* __restrict__ tau, volatile int* ready) {
   extern __shared__ __align__(16) double qcol[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int j = blockIdx.x * 8 + warp;
+  const int j = blockIdx.x * (blockDim.x >> 5) + warp;   // 8 columns per CTA, fewer when 8 do not fit in shared memory
   if (j >= ns) return;
   double* a = qcol + (long)warp * nb;
   double* aj = X + (long)j * nb;
@@ -1226,7 +1337,7 @@ apply_q_smem_kernel(const double* __restrict__ X, const double* __restrict__ tau
                     const double* __restrict__ scale_sig2, const int* __restrict__ rowperm) {
   extern __shared__ __align__(16) double qcol[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i0 = blockIdx.x * 8 + warp;
+  const int i0 = blockIdx.x * (blockDim.x >> 5) + warp;
   if (i0 >= m) return;
   double* y = qcol + (long)warp * nb;
   const double* jc = Jm + (long)perm[i0] * ns;
@@ -1916,7 +2027,11 @@ static int run_qr(cudaStream_t st, SvdWork& w, double* Xq, double* tau, int nb, 
     if (first_on_device(attr)) {
       cudaFuncSetAttribute(qr_dataflow_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     }
-    qr_dataflow_smem_kernel<<<(ns + 7) / 8, 256, (size_t)8 * nb * sizeof(double), st>>>(Xq, nb, ns, tau, w.ready);
+    // columns per CTA: as many of 8 as fit in 200 KB (20 m rows at m = 300: 4 columns of 48 KB)
+    int wpb = (int)((200 * 1024) / ((size_t)nb * sizeof(double)));
+    wpb = wpb > 8 ? 8 : (wpb < 1 ? 1 : wpb);
+    qr_dataflow_smem_kernel<<<(ns + wpb - 1) / wpb, 32 * wpb, (size_t)wpb * nb * sizeof(double), st>>>(Xq, nb, ns, tau,
+                                                                                                    w.ready);
   }
   return 0;
 }
@@ -1930,8 +2045,10 @@ static void run_apply_q(cudaStream_t st, const double* Xq, const double* tau, co
     if (first_on_device(attr)) {
       cudaFuncSetAttribute(apply_q_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     }
-    apply_q_smem_kernel<<<(m + 7) / 8, 256, (size_t)8 * nb * sizeof(double), st>>>(Xq, tau, src, perm, nb, ns, m, Yout,
-                                                                               scale_sig2, rowperm);
+    int wpb = (int)((200 * 1024) / ((size_t)nb * sizeof(double)));
+    wpb = wpb > 8 ? 8 : (wpb < 1 ? 1 : wpb);
+    apply_q_smem_kernel<<<(m + wpb - 1) / wpb, 32 * wpb, (size_t)wpb * nb * sizeof(double), st>>>(Xq, tau, src, perm, nb, ns,
+                                                                                              m, Yout, scale_sig2, rowperm);
   }
 }
 
@@ -1957,7 +2074,9 @@ int svd_split(cudaStream_t st, SvdWork& w, const double* Bc, BondGeom g, int dir
   // QR preconditioning pays off from a few dozen columns on; it needs one resident warp per
   // column and the column in registers (nb <= 32*96)
   const int use_qr = (g_svd_precond >= 0) ? g_svd_precond : w.use_qr;
-  const bool qr = (use_qr == 1 || use_qr == 3 || (use_qr == 2 && ns >= 32)) && nb <= 32 * 96 && ns <= 8 * 140;
+  // (the tall columns of a class-C bond live in shared memory: one column must fit in 200 KB)
+  const bool qr = (use_qr == 1 || use_qr == 3 || (use_qr == 2 && ns >= 32)) && (size_t)nb * sizeof(double) <= 200 * 1024 &&
+                  ns <= 8 * 140;
 
   long nJ = (long)ns * ns;
   long ninit = nJ > 8 ? nJ : 8;
@@ -2041,6 +2160,17 @@ int svd_split(cudaStream_t st, SvdWork& w, const double* Bc, BondGeom g, int dir
     svd_scatter_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(w.X, w.J, w.sig2, w.perm, sg, isoIsA, m,
                                                                       Wb_out, Wb1_out);
     nl += 1;
+  }
+  if (hinfo[7] > 0.0) {   // zero singular values among the kept ones: complete the isometry like ITensor does
+    const int nrows = isoIsA ? sg.nA : sg.nB;
+    const size_t sh = (size_t)(nrows + m + 64 + 32) * sizeof(double);
+    if (sh <= 200 * 1024) {
+      static unsigned long long attr = 0;
+      if (first_on_device(attr))
+        cudaFuncSetAttribute(svd_complete_iso_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      svd_complete_iso_kernel<<<1, 1024, sh, st>>>(isoIsA ? Wb_out : Wb1_out, nrows, m, isoIsA ? sg.nlA : 1, isoIsA);
+      nl += 1;
+    }
   }
   if (launches) *launches += nl;
   if (cudaGetLastError() != cudaSuccess) return -2;

@@ -3,6 +3,7 @@
 // Prints "hosttest: PASS" and returns 0, or the first failed check and returns 1.
 #include <cstdio>
 #include <cstdlib>
+#include <sstream>
 
 #include "initial_w.h"
 #include "itensor_lite.h"
@@ -127,6 +128,40 @@ int main() {
     Args a1("lambda", 0.5, "Npass", 4);
     Args a2{a1, "Maxm", 7};
     CHECK(a2.getInt("Npass") == 4 && a2.getInt("Maxm") == 7 && a2.getReal("lambda") == 0.5 && a2.getInt("none", 3) == 3, "Args");
+  }
+  // ---- svd(T, U, S, V, Args) -> Spectrum (fixedL.cc:519-523 call shape), W(c+dc) *= S, Print/PrintData
+  {
+    Index l("l", 3, Link), s1("s1", 2, Site), s2("s2", 2, Site), r("r", 4, Link);
+    std::vector<Real> d(3 * 2 * 2 * 4);
+    for (auto& v : d) v = rnd(seed);
+    ITensor B(std::vector<Index>{l, s1, s2, r}, std::move(d));
+    ITensor U(l, s1), S, V;                 // U shares (l, s1) with B: those are the rows
+    auto spec = svd(B, U, S, V, {"Cutoff", 0.0, "Maxm", 100, "Minm", 1});
+    CHECK(spec.numEigsKept() == 6 && spec.truncerr() == 0.0, "svd keeps min(6,8) values without truncation");
+    ITensor R = U * S * V;
+    CHECK(norm(R - B) < 1e-12 * norm(B), "U*S*V == B");
+    ITensor UU = U * U;                     // contracts every index: sum of squares = number of columns
+    CHECK(std::fabs(UU.data()[0] - 6.0) < 1e-12, "U has orthonormal columns");
+    ITensor Vn = V;
+    Vn *= S;                                // W.Aref(c+dc) *= S (fixedL.cc:521)
+    CHECK(norm(U * Vn - B) < 1e-12 * norm(B), "U*(S*V) == B");
+    ITensor U2(l, s1), S2, V2;
+    auto spec2 = svd(B, U2, S2, V2, {"Cutoff", 0.0, "Maxm", 3, "Minm", 1});
+    double tail = 0;
+    for (int i = 3; i < 6; ++i) tail += spec.eigsKept()[i];
+    CHECK(spec2.numEigsKept() == 3 && std::fabs(spec2.truncerr() - tail) < 1e-12, "truncerr = discarded weight");
+    // rank-deficient: zero singular value kept by Minm still gives an isometry (ITensor semantics)
+    ITensor Z(std::vector<Index>{l, s1, s2, r});
+    Z.set(l(1), s1(1), s2(1), r(1), 2.0);
+    ITensor U3(l, s1), S3, V3;
+    svd(Z, U3, S3, V3, {"Cutoff", 1E-10, "Maxm", 4, "Minm", 4});
+    ITensor UU3 = U3 * U3;
+    CHECK(std::fabs(UU3.data()[0] - 4.0) < 1e-12, "zero singular values: U completed to an isometry");
+    std::ostringstream os;
+    os << l << " " << B;
+    printData(os, Z);
+    CHECK(os.str().find("(l,3,Link)") != std::string::npos && os.str().find("(1,1,1,1) 2.0000000000") != std::string::npos,
+          "Print / PrintData formatting");
   }
   if (fails == 0) printf("hosttest: PASS\n");
   return fails ? 1 : 0;

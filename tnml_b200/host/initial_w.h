@@ -397,6 +397,117 @@ inline RMPS to_raw(itensor::MPS const& W) {
 // ---- the ITensor-shaped entry points fixedL.cc uses on whole MPS (fixedL.cc:697,710,723,729) ----
 namespace itensor {
 
+// svd(T, U, S, V, {"Cutoff", c, "Maxm", m, "Minm", n [, "DoRelCutoff", b]}) -> Spectrum   (fixedL.cc:519-523)
+// ITensor v2 semantics as assumed in SURVEY 8c(1-2): the indices T shares with the incoming U are the
+// rows; U gets orthonormal columns over a new Link index, S is diagonal >= 0 descending, T ~ U*S*V;
+// truncation by truncate_spectrum on sigma^2; Spectrum::truncerr() = discarded weight.  This host
+// version (one-sided Jacobi, float64) serves the small tensors of the host-side code (initial W,
+// tests); the bond update of `fixedL` itself goes through tnml_svd_split on the device.
+class Spectrum {
+  Real truncerr_ = 0;
+  std::vector<Real> eigs_;
+
+ public:
+  Spectrum() {}
+  Spectrum(std::vector<Real> const& eigs, Real terr) : truncerr_(terr), eigs_(eigs) {}
+  Real truncerr() const { return truncerr_; }
+  std::vector<Real> const& eigsKept() const { return eigs_; }
+  int numEigsKept() const { return (int)eigs_.size(); }
+};
+
+inline Spectrum svd(ITensor const& T, ITensor& U, ITensor& S, ITensor& V, Args const& args = Args()) {
+  if (!T) Error("svd of default ITensor");
+  std::vector<Index> rowI, colI;
+  for (auto const& I : T.inds()) {
+    bool inU = false;
+    if (U)
+      for (auto const& J : U.inds()) inU = inU || (J == I);
+    (inU ? rowI : colI).push_back(I);
+  }
+  if (rowI.empty() || colI.empty()) Error("svd: U must share some but not all indices with T");
+  long nr = 1, nc = 1;
+  for (auto const& I : rowI) nr *= I.m();
+  for (auto const& I : colI) nc *= I.m();
+  // M[(rows),(cols)] = T permuted: contract with nothing, just reorder through an identity trick:
+  // walk all elements of T and scatter
+  std::vector<Index> const& ti = T.inds();
+  std::vector<long> stride_out(ti.size());
+  {
+    std::vector<Index> order = rowI;
+    order.insert(order.end(), colI.begin(), colI.end());
+    std::vector<long> ostr(order.size());
+    long sacc = 1;
+    for (int q = (int)order.size() - 1; q >= 0; --q) {
+      ostr[q] = sacc;
+      sacc *= order[q].m();
+    }
+    for (size_t i = 0; i < ti.size(); ++i)
+      for (size_t q = 0; q < order.size(); ++q)
+        if (order[q] == ti[i]) stride_out[i] = ostr[q];
+  }
+  std::vector<Real> M(nr * nc);
+  {
+    std::vector<long> cnt(ti.size(), 0);
+    long dst = 0;
+    for (size_t k = 0; k < T.data().size(); ++k) {
+      M[dst] = T.data()[k];
+      for (int q = (int)ti.size() - 1; q >= 0; --q) {
+        dst += stride_out[q];
+        if (++cnt[q] < ti[q].m()) break;
+        dst -= stride_out[q] * ti[q].m();
+        cnt[q] = 0;
+      }
+    }
+  }
+  std::vector<Real> Um, sv, Vt;
+  initw::svd_small(M, nr, nc, Um, sv, Vt);
+  const long k = (long)sv.size();
+  std::vector<Real> P(k);
+  for (long i = 0; i < k; ++i) P[i] = sv[i] * sv[i];
+  Real terr = 0;
+  const long m = initw::truncate_spectrum(P, args.getInt("Maxm", 1000000), args.getInt("Minm", 1),
+                                          args.getReal("Cutoff", 0.0), args.getBool("DoRelCutoff", false), &terr);
+  // ITensor returns orthonormal U columns also for zero singular values: complete them (Gram-Schmidt
+  // of unit vectors against the columns kept so far)
+  for (long c = 0; c < m; ++c) {
+    Real nn = 0;
+    for (long r = 0; r < nr; ++r) nn += Um[r * k + c] * Um[r * k + c];
+    if (nn > 0.25) continue;
+    for (long e = 0; e < nr; ++e) {
+      std::vector<Real> v(nr, 0.0);
+      v[e] = 1.0;
+      for (int pass = 0; pass < 2; ++pass)
+        for (long c2 = 0; c2 < m; ++c2) {
+          if (c2 == c) continue;
+          Real d = 0;
+          for (long r = 0; r < nr; ++r) d += Um[r * k + c2] * v[r];
+          for (long r = 0; r < nr; ++r) v[r] -= d * Um[r * k + c2];
+        }
+      Real vn = 0;
+      for (Real x : v) vn += x * x;
+      if (vn > 0.25) {
+        vn = std::sqrt(vn);
+        for (long r = 0; r < nr; ++r) Um[r * k + c] = v[r] / vn;
+        break;
+      }
+    }
+  }
+  Index ul("ul", m, Link), vl("vl", m, Link);
+  std::vector<Index> ui = rowI, vi{vl};
+  ui.push_back(ul);
+  vi.insert(vi.end(), colI.begin(), colI.end());
+  std::vector<Real> ud(nr * m), sd(m * m, 0.0), vd(m * nc);
+  for (long r = 0; r < nr; ++r)
+    for (long c = 0; c < m; ++c) ud[r * m + c] = Um[r * k + c];
+  for (long c = 0; c < m; ++c) sd[c * m + c] = sv[c];
+  for (long c = 0; c < m; ++c)
+    for (long j = 0; j < nc; ++j) vd[c * nc + j] = Vt[c * nc + j];
+  U = ITensor(ui, std::move(ud));
+  S = ITensor(std::vector<Index>{ul, vl}, std::move(sd));
+  V = ITensor(vi, std::move(vd));
+  return Spectrum(std::vector<Real>(P.begin(), P.begin() + m), terr);
+}
+
 // overlap(psi, phi) = <psi|phi>, every site (and label) index contracted
 inline Real overlap(MPS const& A, MPS const& B) { return initw::overlap(initw::to_raw(A), initw::to_raw(B)); }
 

@@ -23,6 +23,7 @@
 #include <map>
 #include <sstream>
 #include <stdexcept>
+#include <iostream>
 #include <string>
 #include <vector>
 
@@ -284,6 +285,44 @@ class ITensor {
     return *this;
   }
 };
+// ---- printing (ITensor's Print / PrintData / PAUSE / EXIT macros, util.h and fixedL.cc debugging aids) ----
+inline std::ostream& operator<<(std::ostream& s, Index const& I) {
+  return s << "(" << I.name() << "," << I.m() << "," << I.type().name << ")";
+}
+inline std::ostream& operator<<(std::ostream& s, IndexVal const& iv) { return s << iv.index << "=" << iv.val; }
+inline Real norm(ITensor const& T);
+inline std::ostream& operator<<(std::ostream& s, ITensor const& T) {
+  if (!T) return s << "ITensor r=0: (default constructed)";
+  s << "ITensor r=" << T.r() << ":";
+  for (auto const& I : T.inds()) s << " " << I;
+  return s << "  {norm=" << format("%.2f", norm(T)) << "}";
+}
+// PrintData: every element above 1E-10 with its index values, like ITensor's printData
+inline void printData(std::ostream& s, ITensor const& T) {
+  s << T << "\n";
+  if (!T) return;
+  std::vector<long> cnt(T.inds().size(), 1);
+  for (size_t k = 0; k < T.data().size(); ++k) {
+    if (std::fabs(T.data()[k]) > 1E-10) {
+      s << "  (";
+      for (size_t q = 0; q < cnt.size(); ++q) s << (q ? "," : "") << cnt[q];
+      s << ") " << format("%.10f", T.data()[k]) << "\n";
+    }
+    for (int q = (int)cnt.size() - 1; q >= 0; --q) {
+      if (++cnt[q] <= T.inds()[q].m()) break;
+      cnt[q] = 1;
+    }
+  }
+}
+inline void pause_() {
+  std::cout << "(Paused, press enter to continue)" << std::endl;
+  std::cin.get();
+}
+#define Print(X) (std::cout << #X << " = " << (X) << std::endl)
+#define PrintData(X) (std::cout << #X << " = ", itensor::printData(std::cout, (X)))
+#define PAUSE itensor::pause_();
+#define EXIT exit(0);
+
 inline ITensor operator*(ITensor const& A, ITensor const& B) { return ITensor::contract(A, B); }
 inline ITensor operator*(ITensor A, Real x) { return A *= x; }
 inline ITensor operator*(Real x, ITensor A) { return A *= x; }
