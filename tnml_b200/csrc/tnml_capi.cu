@@ -725,9 +725,40 @@ int advance_env(tnml_handle h, int c, int right) {
   const long rows = pe.fat ? NT * NL : NT;
   const int div = pe.fat ? NL : 1;
   const int J = kout * (w.lab ? NL : 1);
-  krgemm(h->st, 2, pe.p, kin, kin, featp(h, c), nullptr, div, Bm, J, J, ns.p, J, rows, h->num_sm);
-  CKL();
-  h->stats.launches += 1;
+  // Label-carrying environment (10 NT rows: the expensive advance of a leftward class-L / rightward
+  // class-R bond): same tcgen05 int8 kernel as the projection, S = 2 weights, one image per NL rows.
+  // The planes share the projection's buffers (the bond update that used them is over).
+  int variant = h->krgemm_variant;
+  if (variant < 0) {
+    const char* e = getenv("TNML_KRGEMM");
+    variant = e ? atoi(e) : 3;
+  }
+  bool done = false;
+  if (variant == 3 && pe.fat && NT >= 1024 && kin >= 48 && oz_supported(2, kin, h->oz_slices)) {
+    const int nsl = h->oz_slices;
+    TRY(ensure_bytes(h, (void**)&h->oz_A8, h->oz_capA, oz_a8_bytes(rows, 8)));
+    TRY(ensure_bytes(h, (void**)&h->oz_ea, h->oz_capea, (size_t)oz_rows_pad(rows) * sizeof(double)));
+    TRY(ensure_bytes(h, (void**)&h->oz_B8, h->oz_capB, oz_b8_bytes(2, J, 8)));
+    TRY(ensure_bytes(h, (void**)&h->oz_eb, h->oz_capeb, (size_t)oz_cols_pad(2, J) * sizeof(double)));
+    h->oz_tag_bond = -1;   // the projection planes of the finished bond are overwritten
+    oz_slice_rows(h->st, pe.p, kin, kin, rows, nsl, h->oz_A8, h->oz_ea);
+    CKL();
+    oz_slice_cols(h->st, 2, Bm, J, kin, J, nsl, h->oz_B8, h->oz_eb);
+    CKL();
+    if (oz_krgemm(h->st, 2, nsl, h->oz_A8, h->oz_ea, rows, featp(h, c), nullptr, div, h->oz_B8, h->oz_eb, J, ns.p, J,
+                  h->num_sm)) {
+      CKL();
+      h->stats.launches += 3;
+      done = true;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  if (!done) {
+    krgemm(h->st, 2, pe.p, kin, kin, featp(h, c), nullptr, div, Bm, J, J, ns.p, J, rows, h->num_sm);
+    CKL();
+    h->stats.launches += 1;
+  }
   h->stats.alg_flops += (double)rows * 4.0 * kin * J;
   h->stats.alg_bytes += 8.0 * rows * ((double)kin + J);
   ns.m = kout;
