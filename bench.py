@@ -203,7 +203,7 @@ def build_workload(args, rank, world):
     b0, b1 = fixedl.bounds(world, NTg)[rank]
     if args.config == 5:
         pix, labels = data.synthetic_pixels(b1 - b0, 8, seed=20260925, first=b0)
-        feat = data.phi(pix * 255.0)
+        feat = data.phi(pix)                  # same feature map as config 3 (pixels / 255, phi divides by 255 again)
         W = data.window_mps(8, 2, args.maxm, seed=5)
         return feat, labels, W, NTg, b0
     pix, labels = data.synthetic_digits(b1 - b0, 14, seed=20260925, first=b0)

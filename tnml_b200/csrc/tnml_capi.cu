@@ -3,6 +3,7 @@
 // No CPU fallback: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX: per-phase ranges for Nsight timelines (no-ops without a tool attached)
 
 #include <algorithm>
 #include <cmath>
@@ -220,12 +221,15 @@ struct PhaseTimer {
   cudaEvent_t a = nullptr, b = nullptr;
   int ph;
   PhaseTimer(tnml_handle h_, int ph_) : h(h_), ph(ph_) {
+    static const char* const names[PH_COUNT] = {"tnml:proj", "tnml:grad", "tnml:fat", "tnml:svd", "tnml:shift", "tnml:other"};
+    nvtxRangePushA(names[ph]);
     if (!h->timing) return;
     a = get();
     b = get();
     cudaEventRecord(a, h->st);
   }
   ~PhaseTimer() {
+    nvtxRangePop();
     if (!h->timing) return;
     cudaEventRecord(b, h->st);
     h->evs.push_back({ph, a, b});

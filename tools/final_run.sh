@@ -1,7 +1,8 @@
 #!/bin/bash
 # Round-end measurement pass on the GPU box (one GPU): tests, bench line, BASELINE configs, full-sweep
 # diagnostics, ncu evidence.  Outputs land in gpurun_out/ (scratch) and profiles/ (tracked).
-TAG=${1:-r01}
+TAG=${1:-r02}
+export TNML_PROFILE_TAG=${TAG}
 mkdir -p gpurun_out
 (timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -4) > gpurun_out/final_pytest.log
 timeout 400 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err

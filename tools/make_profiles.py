@@ -25,6 +25,11 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_tensor_op_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed_op_tma_ld.sum", "smsp__sass_inst_executed_op_utcmma.sum",
+        "smsp__sass_inst_executed_op_tmem_ldt.sum", "sm__cycles_active.avg", "sm__cycles_elapsed.avg.per_second",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "dram__cycles_active.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
@@ -91,6 +96,26 @@ for rp in reps:
     for k, v in s.items():
         md.append(f"* {k}: {v}")
     md.append("")
+# what bench.py's roofline.traffic reads: dram bytes of one launch of the dominant kernel, the NT it was
+# captured at and the commit of the build
+def _bytes(x):
+    v, u = x.split()[0], x.split()[1] if len(x.split()) > 1 else "byte"
+    f = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1.0)
+    return float(v.replace(",", "")) * f
+
+
+try:
+    summary["commit"] = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True,
+                                       cwd=ROOT).stdout.strip()
+except Exception:
+    summary["commit"] = "?"
+if "oz_gemm" in summary["kernels"]:
+    k = summary["kernels"]["oz_gemm"]
+    try:
+        k["dram_bytes"] = _bytes(k["dram__bytes_read.sum"]) + _bytes(k["dram__bytes_write.sum"])
+        k["NT"] = 30000
+    except Exception:
+        pass
 json.dump(summary, open(os.path.join(out, f"{tag}_ncu_summary.json"), "w"), indent=1)
 open(os.path.join(out, f"{tag}_ncu_summary.md"), "w").write("\n".join(md) + "\n")
 print("wrote", os.path.join(out, f"{tag}_ncu_summary.md"))

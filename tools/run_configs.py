@@ -20,7 +20,8 @@ sys.path.insert(0, ROOT)
 from oracle import fixedl_oracle as O  # noqa: E402   (checker)
 from tnml_b200 import capi, data, fixedl  # noqa: E402
 
-out = open(os.path.join(ROOT, "profiles", "configs_r01.txt"), "a")
+TAG = os.environ.get("TNML_PROFILE_TAG", "r02")
+out = open(os.path.join(ROOT, "profiles", f"configs_{TAG}.txt"), "a")
 
 
 def say(*a):
