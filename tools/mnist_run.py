@@ -9,7 +9,7 @@ git-ignored, staged from the reference's mllib/MNIST by `mkdir -p baseline/_ref/
       float64 summation orders of the oracle (1 and 4 ParallelDo shards) -- their spread is the
       reference algorithm's own reproducibility.
 
-  python tools/mnist_run.py [nsweep=3]            -> profiles/mnist_<tag>.txt
+  python tools/mnist_run.py [nsweep=3]            -> gpurun_out/mnist_<tag>.txt (copy to profiles/)
 """
 import os
 import sys
