@@ -7,9 +7,8 @@ mkdir -p gpurun_out
 (timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -4) > gpurun_out/final_pytest.log
 timeout 400 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
 timeout 200 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
-rm -f profiles/configs_${TAG}.txt
+rm -f gpurun_out/configs_${TAG}.txt
 timeout 400 python tools/run_configs.py 1 300 2 3 > gpurun_out/configs.log 2>&1
-cp profiles/configs_${TAG}.txt gpurun_out/ 2>/dev/null
 rm -f gpurun_out/sweep_diag.txt
 timeout 300 python tools/sweep_diag.py 60000 120 4 > gpurun_out/diag_final.log 2>&1
 cp gpurun_out/sweep_diag.txt gpurun_out/sweeps_${TAG}.txt

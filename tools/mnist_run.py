@@ -23,7 +23,8 @@ from tnml_b200 import capi, data, fixedl  # noqa: E402
 
 TAG = os.environ.get("TNML_PROFILE_TAG", "r02")
 MN = os.path.join(ROOT, "baseline", "_ref", "MNIST")
-out = open(os.path.join(ROOT, "profiles", f"mnist_{TAG}.txt"), "w")
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+out = open(os.path.join(ROOT, "gpurun_out", f"mnist_{TAG}.txt"), "w")   # copied to profiles/ afterwards: only gpurun_out/ travels back
 
 
 def say(*a):

@@ -21,7 +21,8 @@ from oracle import fixedl_oracle as O  # noqa: E402   (checker)
 from tnml_b200 import capi, data, fixedl  # noqa: E402
 
 TAG = os.environ.get("TNML_PROFILE_TAG", "r02")
-out = open(os.path.join(ROOT, "profiles", f"configs_{TAG}.txt"), "a")
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+out = open(os.path.join(ROOT, "gpurun_out", f"configs_{TAG}.txt"), "a")   # copied to profiles/ afterwards
 
 
 def say(*a):
