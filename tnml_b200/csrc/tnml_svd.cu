@@ -633,13 +633,18 @@ __device__ __forceinline__ void rr_where(int n, int r, int x, int& k, int& slot)
   }
 }
 
-template <int W>
-__global__ void __launch_bounds__(32 * W, 1)
+// NTH threads per CTA: the rotation rounds are a latency chain run by the first NTR = 32 W threads
+// (their mapping needs exactly 2W x 2W threads); the Gram and apply phases are throughput work and use
+// all NTH / 32 warps (16 warps: Gram 1.7k -> 0.9k cycles, apply 3.7k -> 1.9k per block pairing).
+template <int W, int NTH>
+__global__ void __launch_bounds__(NTH, 1)
 jacobi_cluster_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows, int ns, int ld, int nblk_e,
                       double tol2, double conv, int max_sweeps, int cross_only, double* __restrict__ info,
                       double* __restrict__ sweepmax, int* __restrict__ flags) {
   namespace cg = cooperative_groups;
-  constexpr int NC = 2 * W, NR = NC - 1, NTH = 32 * W, NWARP = NTH / 32, TG = NC / 8;
+  constexpr int NC = 2 * W, NR = NC - 1, NTR = 32 * W, NWARP = NTH / 32, TG = NC / 8;
+  constexpr int KH = NWARP / (TG * TG);   // k-splits of the Gram products (partial sums in G0..G[KH-1])
+  static_assert(KH >= 1 && KH <= 4 && NWARP == KH * TG * TG, "Gram phase: warps = tiles x k-splits");
   static_assert(W == 8, "cluster kernel is written for 8-column blocks (256 threads)");
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
@@ -650,7 +655,8 @@ jacobi_cluster_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows,
   double* buf1 = sm + (long)NC * ld;                 // [NC][ld]
   double* G0 = buf1 + (long)NC * ld;                 // [NC][GLD]
   double* G1 = G0 + NC * GLD;
-  double* RA = G1 + NC * GLD;
+  double* GX = G1 + NC * GLD;                        // [2][NC][GLD] extra Gram partials (KH = 4)
+  double* RA = GX + 2 * NC * GLD;
   double* CS = RA + NC * GLD;                        // [2][W][2]
   double** DST = reinterpret_cast<double**>(CS + 4 * W);   // [NC] destination column of the next round
   // inner tournaments: "full" = all pairs of the 16 staged columns (15 rounds), used for the first
@@ -760,7 +766,7 @@ jacobi_cluster_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows,
           const int tile = warp % (TG * TG), kh = warp / (TG * TG);
           const int ti = tile / TG, tj = tile - ti * TG;
           const int nk4 = (rows + 3) >> 2;
-          const int kbeg = (nk4 * kh) / 2, kend = (nk4 * (kh + 1)) / 2;
+          const int kbeg = (nk4 * kh) / KH, kend = (nk4 * (kh + 1)) / KH;
           const double* pa = S + (long)(ti * 8 + g) * ld + t;
           const double* pb = S + (long)(tj * 8 + g) * ld + t;
           double d[4][2];
@@ -780,14 +786,17 @@ jacobi_cluster_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows,
             const bool ok = (r0 + t) < rows;
             dmma884s(d[0][0], d[0][1], ok ? pa[r0] : 0.0, ok ? pb[r0] : 0.0);
           }
-          double* Gd = kh ? G1 : G0;
+          double* Gd = (kh == 0) ? G0 : (kh == 1 ? G1 : GX + (kh - 2) * NC * GLD);
           Gd[(ti * 8 + g) * GLD + tj * 8 + 2 * t] = (d[0][0] + d[1][0]) + (d[2][0] + d[3][0]);
           Gd[(ti * 8 + g) * GLD + tj * 8 + 2 * t + 1] = (d[0][1] + d[1][1]) + (d[2][1] + d[3][1]);
         }
         __syncthreads();
-        {
-          const int r = tid / NC, c = tid - r * NC;   // NTH == NC * NC
-          G0[r * GLD + c] += G1[r * GLD + c];
+        if (tid < NC * NC) {
+          const int r = tid / NC, c = tid - r * NC;
+          double acc = G0[r * GLD + c];
+          if (KH > 1) acc += G1[r * GLD + c];
+          if (KH > 2) acc += GX[r * GLD + c] + GX[NC * GLD + r * GLD + c];
+          G0[r * GLD + c] = acc;
         }
         __syncthreads();
         // ---- rotation rounds on the Gram matrix (identical to jacobi_gram_kernel)
@@ -806,7 +815,7 @@ jacobi_cluster_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows,
         __syncthreads();
         constexpr int RE = 2;
         constexpr int T_BLK = W * W, T_RA = NC * W / RE;
-        static_assert(T_BLK + T_RA + W <= NTH, "thread budget");
+        static_assert(T_BLK + T_RA + W <= NTR, "thread budget");
         for (int rd = 0; rd < nir; ++rd) {
           const double* cs = CS + (rd & 1) * 2 * W;
           double* csn = CS + ((rd + 1) & 1) * 2 * W;
@@ -835,8 +844,8 @@ jacobi_cluster_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows,
               RA[i * GLD + pl] = cl * a - sl * b;
               RA[i * GLD + ql] = sl * a + cl * b;
             }
-          } else if (tid >= NTH - W && rd + 1 < nir) {
-            const int j = tid - (NTH - W);
+          } else if (tid >= NTR - W && tid < NTR && rd + 1 < nir) {
+            const int j = tid - (NTR - W);
             const unsigned la = LA[rd * W + j];
             const int xp = la & 0xf, xq = (la >> 4) & 0xf, yp = (la >> 8) & 0xf, yq = (la >> 12) & 0xf;
             const int kx = (la >> 16) & 0xf, ky = (la >> 20) & 0xf;
@@ -907,7 +916,7 @@ jacobi_cluster_kernel(double* __restrict__ A, double* __restrict__ Jm, int rows,
       R = Rn;
     }
     // ---- end of sweep: largest rotated cos^2 over the cluster
-    if (active && (tid < W || tid >= NTH - W) && mo > 0.0) atomic_max_pos(sweepmax + sw, mo);
+    if (active && (tid < W || (tid >= NTR - W && tid < NTR)) && mo > 0.0) atomic_max_pos(sweepmax + sw, mo);
     __threadfence();
     cluster.sync();
     const double smax = __ldcg(sweepmax + sw);
@@ -1819,8 +1828,8 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
     const char* e = getenv("TNML_SVD_CLUSTER");
     use_cluster = e ? atoi(e) : 1;
     if (use_cluster) {
-      if (cudaFuncSetAttribute(jacobi_cluster_kernel<8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
-          cudaFuncSetAttribute(jacobi_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
+      if (cudaFuncSetAttribute(jacobi_cluster_kernel<8, 512>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+          cudaFuncSetAttribute(jacobi_cluster_kernel<8, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
         cudaGetLastError();
         use_cluster = 0;
       }
@@ -1828,13 +1837,13 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
   }
   const bool want_cluster = (g_svd_cluster >= 0) ? (g_svd_cluster != 0 && use_cluster >= 0 && use_cluster != 0) : (use_cluster != 0);
   if (gram && want_cluster && GW == 8 && nblk_e <= 32) {
-    const size_t need_cl = ((size_t)2 * 16 * gld + 3 * 16 * GLD + 4 * 8) * sizeof(double) + 16 * sizeof(double*) +
+    const size_t need_cl = ((size_t)2 * 16 * gld + 5 * 16 * GLD + 4 * 8) * sizeof(double) + 16 * sizeof(double*) +
                            (size_t)(15 + 8) * 8 * sizeof(unsigned short) + (size_t)(15 + 8) * 16 +
                            (size_t)(14 + 7) * 8 * sizeof(unsigned) + 32;
     if (need_cl <= 220 * 1024) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(16, 1, 1);
-      cfg.blockDim = dim3(256, 1, 1);
+      cfg.blockDim = dim3(512, 1, 1);
       cfg.dynamicSmemBytes = need_cl;
       cfg.stream = st;
       cudaLaunchAttribute at[1];
@@ -1846,7 +1855,7 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
       cfg.numAttrs = 1;
       if (!w.cluster_checked) {
         int ncl = 0;
-        if (cudaOccupancyMaxActiveClusters(&ncl, jacobi_cluster_kernel<8>, &cfg) != cudaSuccess || ncl < 1) {
+        if (cudaOccupancyMaxActiveClusters(&ncl, jacobi_cluster_kernel<8, 512>, &cfg) != cudaSuccess || ncl < 1) {
           cudaGetLastError();
           use_cluster = 0;
         }
@@ -1860,7 +1869,7 @@ static int jacobi_iterate(cudaStream_t st, SvdWork& w, double* A, double* Jm, in
           cross_only = e ? atoi(e) : 1;
         }
         const int cross_now = (g_svd_cross >= 0) ? g_svd_cross : cross_only;
-        if (cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<8>, A, Jm, rows, ns, gld, nblk_e, tol2, conv, max_sweeps,
+        if (cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<8, 512>, A, Jm, rows, ns, gld, nblk_e, tol2, conv, max_sweeps,
                                cross_now, w.info, w.sweepmax, w.flags) == cudaSuccess) {
           nl += 2;
           return 1;   // convergence flag is in info[6]: the caller reads it with the truncation results (one sync)
