@@ -654,12 +654,6 @@ int grad_from_P(tnml_handle h, const double* X, double lambda) {
   return finish_grad(h, X, lambda);
 }
 
-int ddot(tnml_handle h, long n, const double* x, const double* y, double* out) {
-  dot(h->st, n, x, y, h->dot_scratch, h->dscal + 16);
-  CKL();
-  h->stats.launches += 2;
-  return fetch(h, h->dscal + 16, 1, out);
-}
 
 // `reserve` >= bytes: size to allocate when the slot has to grow.  During sweeps the link dims
 // grow towards maxm; growing a slot means a fresh cudaMallocAsync of up to 0.6 GB (measured:
@@ -794,7 +788,7 @@ int set_site_dev(tnml_handle h, int j, int ml, int mr, int lab) {
 
 extern "C" {
 
-const char* tnml_version(void) { return "tnml_b200 0.1 (sm_100a, float64, block-Jacobi SVD)"; }
+const char* tnml_version(void) { return "tnml_b200 0.2 (sm_100a, float64 results: tcgen05 int8 error-free projection + DMMA gradient, cluster Jacobi SVD)"; }
 
 const char* tnml_last_error(tnml_handle h) { return h ? h->err.c_str() : g_err.c_str(); }
 

@@ -13,18 +13,25 @@
 // and only the final combination sum_L 2^(-7(L+2)) acc_L rounds, in float64, like an FMA chain would.
 // With NS = 8 the dropped tail is 2^-57 of (row max) x (column max): float64 GEMM accuracy.
 //
-// Mapping (one persistent CTA per SM, 6 warps, warp-specialised):
-//   * tile = 128 rows x 32 columns (S weight indices x 32/S output columns) x NS accumulator levels;
+// Mapping (one persistent CTA per SM, 19 warps, warp-specialised; see the comments at each role):
+//   * tile = 128 rows x 32 columns (32/S output columns x S weight indices) x NS accumulator levels;
 //     level L of a tile lives in TMEM columns [32L, 32L+32): the MMA of A-slice i multiplies it with
 //     the B slices 0..NS-1-i at once -- they are contiguous in shared memory, so this is ONE
 //     tcgen05.mma with N = 32(NS-i) whose 32-column groups land on levels i..NS-1.  36 slice products
 //     = 8 instructions per 32-deep k-step.
-//   * A (all NS slices of 128 rows, 16 KB each, 128B-swizzled K-major) stays resident in shared
-//     memory for every column tile of the row tile; it is refilled slice by slice (TMA, one mbarrier
-//     per slice) as soon as the last column tile's MMAs of that slice have retired.
-//   * B column tiles (NS x 32 rows x 128 B = 32 KB) stream through a 2-stage TMA ring from L2.
-//   * two TMEM accumulator buffers (2 x 256 columns): the epilogue warps (tcgen05.ld, int32 ->
-//     float64, level combination, output-side Khatri-Rao weights, store) overlap the next tile's MMAs.
+//   * warp 0: TMA producer.  A (all NS slices of 128 rows, 16 KB each, 128B-swizzled K-major) stays
+//     resident in shared memory for every column tile of the row tile and is refilled slice by slice
+//     (one mbarrier per slice) as soon as the last column tile's MMAs of that slice have retired;
+//     B column tiles (NS x 32 rows x 128 B = 32 KB) stream through a 2-stage ring from L2.
+//   * warps 1-2: MMA issuers (even / odd A slices; accumulators are handed over zeroed, so the
+//     order of the two warps' instructions in the tensor pipe does not matter).
+//   * warps 3-18: epilogue (tcgen05.ld of all levels, exact integer merge, float64 combination with
+//     the column scale and the output-side Khatri-Rao weights, store), overlapping the next tile's
+//     MMAs through two TMEM accumulator buffers (2 x 256 columns).
+// Measured cost model (tools/umma_bench.cu, B200): a kind::i8 M=128 K=32 instruction takes
+// max(N/2, 32 + N/4) cycles (shared-memory operand bandwidth below N = 128); FP64 instructions of
+// other warps are throttled ~20x while tcgen05.mma is in flight (47 vs 2.3 cycles per warp
+// instruction; FP32 and integer are not) -- hence the integer-heavy epilogue.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -106,27 +113,6 @@ __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -136,14 +122,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 __device__ __forceinline__ void tmem_st8_zero(uint32_t taddr) {
   const uint32_t z = 0u;
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z) : "memory");
-}
-__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
-  const uint32_t z = 0u;
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
-      "r"(z)
-      : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -161,10 +139,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 // instruction descriptor: S32 accumulate, signed 8-bit A and B, both K-major, M = 128, N = n
 __device__ __forceinline__ uint32_t umma_idesc_i8(int n) {
   return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(OZ_TM >> 4) << 24);
-}
-// exact int32 -> double (|x| < 2^31) without the conversion pipe: 2^52 + 2^31 + x, minus the bias
-__device__ __forceinline__ double i2d(int x) {
-  return __hiloint2double(0x43300000, (int)((unsigned)x ^ 0x80000000u)) - 4503601774854144.0;
 }
 // exact int64 -> double for |x| < 2^51: the bits of 1.5 * 2^52 + x, minus the bias
 __device__ __forceinline__ double ll2d(long long x) {

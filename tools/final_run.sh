@@ -12,6 +12,9 @@ timeout 400 python tools/run_configs.py 1 300 2 3 > gpurun_out/configs.log 2>&1
 rm -f gpurun_out/sweep_diag.txt
 timeout 300 python tools/sweep_diag.py 60000 120 4 > gpurun_out/diag_final.log 2>&1
 cp gpurun_out/sweep_diag.txt gpurun_out/sweeps_${TAG}.txt
+TNML_QR_DEBUG=1 timeout 120 python tools/svd_bench.py > gpurun_out/svd_bench_${TAG}.log 2>&1
+timeout 120 tools/umma_bench > gpurun_out/umma_bench_${TAG}.txt 2>&1
+timeout 200 tools/oz_test > gpurun_out/oz_test_${TAG}.txt 2>&1
 bash tools/profile_run.sh ${TAG} > gpurun_out/profile_run.log 2>&1
 cat gpurun_out/final_pytest.log
 head -c 600 gpurun_out/bench_final.json; echo
