@@ -12,7 +12,7 @@ cap() {  # name regex skip
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -f \
       -o gpurun_out/prof_${TAG}_$1 $B > gpurun_out/ncu_$1.log 2>&1
 }
-cap oz_gemm oz_gemm_kernel 60
+cap oz_gemm oz_gemm_kernel 200   # past the ~95 <8,2> launches of init_envs: a <8,4> projection launch
 cap oz_slice_rows oz_slice_rows_kernel 6
 cap krgram2 krgram2_kernel 5
 cap fat fat_kernel_t 20
