@@ -250,7 +250,7 @@ def test_fixedL_binary_matches_capi(capi, tmp_path):
     D.write_mps_file(str(tmp_path / "W"), W)
     (tmp_path / "in").write_text(
         f"input\n{{\ndatadir = {tmp_path}/d\nNtrain = 20\nimglen = {side}\nNbatch = 4\nmaxm = 6\nminm = 3\n"
-        f"cutoff = 1E-10\nNsweep = 1\nNpass = 3\nnthread = 2\n}}\n")
+        f"cutoff = 1E-10\nNsweep = 1\nNpass = 3\nnthread = 2\ntrace = trace.jsonl\ntrace_phases = yes\n}}\n")
     r = subprocess.run([binp, "in"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     costs = [float(x) for x in re.findall(r"--> After SVD, Cost = ([0-9.eE+-]+)", r.stdout)]
@@ -264,6 +264,13 @@ def test_fixedL_binary_matches_capi(capi, tmp_path):
         assert res.newm == ms[k]
         assert abs(res.cost / 200 - costs[k]) < 2e-10 + 1e-9 * costs[k], k    # printed with 10 decimals
     assert "Before starting DMRG Cost" in r.stdout and "Writing W to disk" in r.stdout
+    # per-bond JSONL trace: one parseable line per bond update, same numbers as the log
+    import json
+    tr = [json.loads(l) for l in (tmp_path / "trace.jsonl").read_text().splitlines()]
+    assert len(tr) == len(costs)
+    for k, t in enumerate(tr):
+        assert t["newm"] == ms[k] and abs(t["cost"] - costs[k]) < 1e-9 and t["launches"] > 0 and t["wall_ms"] > 0
+        assert set(t["phase_ms"]) == {"proj", "grad", "fat", "svd", "shift", "other"} and t["phase_ms"]["svd"] > 0
     # the trained W written by fixedL is then evaluated by the drop-in `fulltest` program
     D.write_idx_files(str(tmp_path / "d"), u8, labels, side, kind="t10k")
     ft = os.path.join(root, "tnml_b200", "host", "fulltest")

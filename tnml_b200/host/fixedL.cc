@@ -14,6 +14,9 @@
 //     SURVEY F7).  `initial = random` selects a seeded random MPS of bond dimension `minitial`
 //     instead; `init_only = yes` stops after writing `W` (no GPU needed).
 //   * `W` / `sites` files use this program's own binary format.
+//   * `trace = <file>` appends one JSON line per bond update (sweep, bond, link dimensions, truncation
+//     error, cost, #correct, wall time, kernel launches, algorithmic bytes / flops from tnml_get_stats;
+//     `trace_phases = yes` adds the CUDA-event phase times) next to the reference's log lines.
 //   * nthread/Nbatch are accepted and validated like the reference but the
 //     parallelism is GPUs: one process per GPU (TNML_RANK / TNML_WORLD_SIZE),
 //     images sharded with ParallelDo's bounds (paralleldo.h:32-43).
@@ -188,7 +191,7 @@ class TrainStates {
 // Compute squared distance of the actual output of the model from the ideal
 // output (fixedL.cc:280-344).  B lives on the device: use_sites selects
 // newB = W.A(c)*W.A(c+dc) (fixedL.cc:527,532) or the current bond tensor.
-Real quadcost(bool use_sites, TrainStates const& ts, Args const& args = Args::global()) {
+Real quadcost(bool use_sites, TrainStates const& ts, Args const& args = Args::global(), int64_t* ncor_out = nullptr) {
   auto h_ = ts.h_;
   auto NT = ts.size();
   auto lambda = args.getReal("lambda", 0.);
@@ -198,6 +201,7 @@ Real quadcost(bool use_sites, TrainStates const& ts, Args const& args = Args::gl
   TN(tnml_quadcost(h_, use_sites ? 1 : 0, lambda, &C, CL, &ncor));
   if (showlabels)
     for (size_t l = 0; l < NL; ++l) printfln("  Label l=%d C%d = %.10f", (int)l, (int)l, CL[l] / NT);
+  if (ncor_out) *ncor_out = ncor;
   long ninc = NT - ncor;
   printfln("Percent correct = %.4f%%, # incorrect = %d/%d", ncor * 100. / NT, (int)ninc, (int)(ncor + ninc));
   return C;
@@ -234,6 +238,16 @@ void mldmrg(MPS& W, TrainStates& ts, Sweeps const& sweeps, Args args) {
   auto pause_step = args.getBool("PauseStep", false);
   auto do_rel = args.getBool("DoRelCutoff", false);
   auto cargs = Args{args, "Normalize", false};
+  // per-bond JSONL trace (rank 0): off unless the input file names a `trace` file
+  FILE* trace = nullptr;
+  auto tracefile = args.getString("Trace", "");
+  auto trace_phases = args.getBool("TracePhases", false);
+  if (!tracefile.empty() && ts.rank_ == 0) {
+    trace = std::fopen(tracefile.c_str(), "a");
+    if (!trace) Error(format("cannot open trace file \"%s\"", tracefile.c_str()));
+  }
+  if (trace && trace_phases) TN(tnml_set_timing(h_, 1));
+  tnml_stats st;
 
   for (int sw = 1; sw <= sweeps.nsweep(); ++sw) {
     printfln("\nSweep %d maxm=%d minm=%d", sw, sweeps.maxm(sw), sweeps.minm(sw));
@@ -241,6 +255,8 @@ void mldmrg(MPS& W, TrainStates& ts, Sweeps const& sweeps, Args args) {
       auto c = (ha == 1) ? b : b + 1;
       auto dc = (ha == 1) ? +1 : -1;
       (void)dc;
+      auto tb0 = std::chrono::steady_clock::now();
+      if (trace) TN(tnml_get_stats(h_, &st, 1));
       ts.setBond(b);
       printfln("Sweep %d Half %d Bond %d", sw, ha, c);
       int origm = 0;
@@ -262,11 +278,30 @@ void mldmrg(MPS& W, TrainStates& ts, Sweeps const& sweeps, Args args) {
       printfln("Original m=%d, New m=%d", origm, newm);
 
       auto largs = Args{cargs, "ShowLabels", true, "lambda", args.getReal("lambda", 0.)};
-      auto newC = quadcost(true, ts, largs);
+      int64_t ncor = 0;
+      auto newC = quadcost(true, ts, largs, &ncor);
       printfln("--> After SVD, Cost = %.10f", newC / NT);
 
       // Update E's (MPS environment tensors)
       ts.shiftE(W, b, ha == 1 ? Fromleft : Fromright);
+      if (trace) {
+        TN(tnml_synchronize(h_));
+        double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count();
+        TN(tnml_get_stats(h_, &st, 0));
+        std::fprintf(trace,
+                     "{\"sweep\": %d, \"half\": %d, \"bond\": %d, \"b\": %d, \"origm\": %d, \"newm\": %d, \"truncerr\": %.6e, "
+                     "\"cost\": %.12e, \"ncorrect\": %lld, \"NT\": %d, \"wall_ms\": %.4f, \"launches\": %lld, "
+                     "\"alg_bytes\": %.6e, \"alg_flops\": %.6e",
+                     sw, ha, c, b, origm, newm, truncerr, newC / NT, (long long)ncor, (int)NT, ms, (long long)st.launches,
+                     st.alg_bytes, st.alg_flops);
+        if (trace_phases)
+          std::fprintf(trace,
+                       ", \"phase_ms\": {\"proj\": %.4f, \"grad\": %.4f, \"fat\": %.4f, \"svd\": %.4f, \"shift\": %.4f, "
+                       "\"other\": %.4f}",
+                       st.ms_proj, st.ms_grad, st.ms_fat, st.ms_svd, st.ms_shift, st.ms_other);
+        std::fprintf(trace, "}\n");
+        std::fflush(trace);
+      }
 
       // Sentinel files (fixedL.cc:542-559).  The reference is ONE process; here rank 0 alone looks at
       // (and removes) the files and its findings are broadcast, so that every rank writes W at the
@@ -308,6 +343,7 @@ void mldmrg(MPS& W, TrainStates& ts, Sweeps const& sweeps, Args args) {
     for (int j = 1; j <= N; ++j) ts.download(W, j);
     if (ts.rank_ == 0) writeToFile("W", W);
   }  // loop over sweeps
+  if (trace) std::fclose(trace);
 }
 
 // ---- deterministic initial W (replaces fixedL.cc:702-728) ---------------------
@@ -445,6 +481,8 @@ int main(int argc, const char* argv[]) {
     auto dorel = input.getYesNo("dorelcutoff", false);
     auto initial = input.getString("initial", "sum");
     auto init_only = input.getYesNo("init_only", false);
+    auto tracefile = input.getString("trace", "");
+    auto trace_phases = input.getYesNo("trace_phases", false);
 
     int rank = std::getenv("TNML_RANK") ? atoi(std::getenv("TNML_RANK")) : 0;
     int world = std::getenv("TNML_WORLD_SIZE") ? atoi(std::getenv("TNML_WORLD_SIZE")) : 1;
@@ -572,7 +610,8 @@ int main(int argc, const char* argv[]) {
 
     auto sweeps = Sweeps(Nsweep, minm, maxm, cutoff);
     auto args = Args{"lambda", lambda, "Method",  method,  "Npass",     Npass,      "alpha",       alpha, "clip",
-                     clip,     "cconv", cconv, "Replace", replace, "PauseStep", pause_step, "DoRelCutoff", dorel};
+                     clip,     "cconv", cconv, "Replace", replace, "PauseStep", pause_step, "DoRelCutoff", dorel,
+                     "Trace", tracefile, "TracePhases", trace_phases};
     auto t0 = std::chrono::steady_clock::now();
     mldmrg(W, ts, sweeps, args);
     double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
