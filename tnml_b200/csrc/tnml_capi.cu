@@ -130,6 +130,7 @@ struct tnml_handle_s {
   size_t oz_capB = 0, oz_capeb = 0;
   long oz_tag_bond = -1, oz_tag_gen = -1;   // (bond, env generation) the planes in oz_A8 belong to
   int oz_tag_ns = 0;
+  const double* oz_tag_ptr = nullptr;       // ... and the environment they were cut from
   long env_gen = 0;                          // bumped whenever an environment slot is (re)written
   int oz_slices = 8;                         // 8: float64-class accuracy (2^-57 of row max x column max)
   int krgemm_variant = -1;                   // -1 default (3 where supported), 3 tcgen05, 2 DMMA persistent, 1 register-staged
@@ -448,6 +449,22 @@ int ensure_bytes(tnml_handle h, void** p, size_t& cap, size_t bytes) {
   return 0;
 }
 
+// plane buffers of the tcgen05 kernels for `rows` operand rows and S*J operand columns; a re-allocation
+// of the row planes drops the tag that says which environment they hold
+int oz_buffers(tnml_handle h, long rows, int S, int J) {
+  const int8_t* before = h->oz_A8;
+  TRY(ensure_bytes(h, (void**)&h->oz_A8, h->oz_capA, oz_a8_bytes(rows, 8)));
+  TRY(ensure_bytes(h, (void**)&h->oz_ea, h->oz_capea, (size_t)oz_rows_pad(rows) * sizeof(double)));
+  TRY(ensure_bytes(h, (void**)&h->oz_B8, h->oz_capB, oz_b8_bytes(S, J, 8)));
+  TRY(ensure_bytes(h, (void**)&h->oz_eb, h->oz_capeb, (size_t)oz_cols_pad(S, J) * sizeof(double)));
+  if (h->oz_A8 != before) h->oz_tag_bond = -1;
+  return 0;
+}
+// true if oz_A8 already holds the planes of environment `env` (cut for this bond, no advance since)
+bool oz_planes_valid(tnml_handle h, const double* env, int ns) {
+  return h->oz_tag_bond == h->currb && h->oz_tag_gen == h->env_gen && h->oz_tag_ns == ns && h->oz_tag_ptr == env;
+}
+
 // Q[n][j] = sum_p w_p(n) sum_a thin[n][a] X[(a*4+p)*J + j]: the projection half of P = B * t.v
 // (fixedL.cc:318,377,399,416).  Default: tcgen05 int8 kernel on error-free 7-bit planes -- the planes
 // of the thin environment are cut once per bond (it does not change during the bond update), those
@@ -461,17 +478,14 @@ int project(tnml_handle h, const double* thin, int mt, const double* f1, const d
   }
   const int ns = h->oz_slices;
   if (variant == 3 && NT >= 1024 && mt >= 48 && oz_supported(4, mt, ns)) {
-    const size_t wantA = oz_a8_bytes(NT, 8);
-    TRY(ensure_bytes(h, (void**)&h->oz_A8, h->oz_capA, wantA));
-    TRY(ensure_bytes(h, (void**)&h->oz_ea, h->oz_capea, (size_t)oz_rows_pad(NT) * sizeof(double)));
-    TRY(ensure_bytes(h, (void**)&h->oz_B8, h->oz_capB, oz_b8_bytes(4, J, 8)));
-    TRY(ensure_bytes(h, (void**)&h->oz_eb, h->oz_capeb, (size_t)oz_cols_pad(4, J) * sizeof(double)));
-    if (h->oz_tag_bond != h->currb || h->oz_tag_gen != h->env_gen || h->oz_tag_ns != ns) {
+    TRY(oz_buffers(h, NT, 4, J));
+    if (!oz_planes_valid(h, thin, ns)) {
       oz_slice_rows(h->st, thin, mt, mt, NT, ns, h->oz_A8, h->oz_ea);
       CKL();
       h->oz_tag_bond = h->currb;
       h->oz_tag_gen = h->env_gen;
       h->oz_tag_ns = ns;
+      h->oz_tag_ptr = thin;
       h->stats.launches += 1;
     }
     oz_slice_cols(h->st, 4, X, J, mt, J, ns, h->oz_B8, h->oz_eb);
@@ -723,30 +737,34 @@ int advance_env(tnml_handle h, int c, int right) {
   const long rows = pe.fat ? NT * NL : NT;
   const int div = pe.fat ? NL : 1;
   const int J = kout * (w.lab ? NL : 1);
-  // Label-carrying environment (10 NT rows: the expensive advance of a leftward class-L / rightward
-  // class-R bond): same tcgen05 int8 kernel as the projection, S = 2 weights, one image per NL rows.
-  // The planes share the projection's buffers (the bond update that used them is over).
+  // Same tcgen05 int8 kernel as the projection, S = 2 weights.  Label-carrying previous environment (10 NT
+  // rows, one image per NL rows: the expensive advance of a leftward class-L / rightward class-R bond): its
+  // planes are cut here, into the projection's buffers (the bond update that used them is over).  Thin
+  // previous environment: it is the operand the finished bond update projected with, so its planes are
+  // normally still there (tags) and the advance costs one kernel over NT rows.
   int variant = h->krgemm_variant;
   if (variant < 0) {
     const char* e = getenv("TNML_KRGEMM");
     variant = e ? atoi(e) : 3;
   }
   bool done = false;
-  if (variant == 3 && pe.fat && NT >= 1024 && kin >= 48 && oz_supported(2, kin, h->oz_slices)) {
+  if (variant == 3 && hasPrev && NT >= 1024 && kin >= 48 && oz_supported(2, kin, h->oz_slices)) {
     const int nsl = h->oz_slices;
-    TRY(ensure_bytes(h, (void**)&h->oz_A8, h->oz_capA, oz_a8_bytes(rows, 8)));
-    TRY(ensure_bytes(h, (void**)&h->oz_ea, h->oz_capea, (size_t)oz_rows_pad(rows) * sizeof(double)));
-    TRY(ensure_bytes(h, (void**)&h->oz_B8, h->oz_capB, oz_b8_bytes(2, J, 8)));
-    TRY(ensure_bytes(h, (void**)&h->oz_eb, h->oz_capeb, (size_t)oz_cols_pad(2, J) * sizeof(double)));
-    h->oz_tag_bond = -1;   // the projection planes of the finished bond are overwritten
-    oz_slice_rows(h->st, pe.p, kin, kin, rows, nsl, h->oz_A8, h->oz_ea);
-    CKL();
+    TRY(oz_buffers(h, rows, 2, J));
+    int nl = 2;
+    if (pe.fat || !oz_planes_valid(h, pe.p, nsl)) {
+      h->oz_tag_bond = -1;   // the planes in the buffer are replaced by this environment's ...
+      oz_slice_rows(h->st, pe.p, kin, kin, rows, nsl, h->oz_A8, h->oz_ea);
+      CKL();
+      ++nl;
+    }
+    h->oz_tag_bond = -1;     // ... and no later projection uses them: the environments change below
     oz_slice_cols(h->st, 2, Bm, J, kin, J, nsl, h->oz_B8, h->oz_eb);
     CKL();
     if (oz_krgemm(h->st, 2, nsl, h->oz_A8, h->oz_ea, rows, featp(h, c), nullptr, div, h->oz_B8, h->oz_eb, J, ns.p, J,
                   h->num_sm)) {
       CKL();
-      h->stats.launches += 3;
+      h->stats.launches += nl;
       done = true;
     } else {
       cudaGetLastError();

@@ -166,44 +166,64 @@ __device__ __forceinline__ void kr_weights_oz(const double* __restrict__ f1, con
 // ---- slicing ------------------------------------------------------------------------------------
 // one warp per row of In [rows][ldin] (ma <= 128): ea[row] and NS int8 planes, written as
 // A8[rowtile][slice][128 rows][128 bytes]; rows beyond `rows` and columns beyond ma are zero.
+// A warp takes OZ_RPW consecutive rows per iteration and issues all their loads (two 16-byte loads per
+// lane and row when the rows are 16-byte aligned) before the first row is cut: the kernel streams
+// 8 ma bytes in and 8 x 128 bytes out per row and needs the loads in flight to approach HBM speed.
+constexpr int OZ_RPW = 4;
 __global__ void __launch_bounds__(256) oz_slice_rows_kernel(const double* __restrict__ In, long ldin, int ma, long rows,
                                                             long rows_pad, int ns, int8_t* __restrict__ A8,
                                                             double* __restrict__ ea) {
   const int lane = threadIdx.x & 31;
   const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long nwarp = ((long)gridDim.x * blockDim.x) >> 5;
-  for (long r = warp; r < rows_pad; r += nwarp) {
-    double x[4];
-    double mx = 0.0;
+  const bool vec = ((reinterpret_cast<uintptr_t>(In) & 15) == 0) && ((ldin & 1) == 0);
+  const int a0 = lane * 4;
+  for (long r0 = warp * OZ_RPW; r0 < rows_pad; r0 += nwarp * OZ_RPW) {
+    double x[OZ_RPW][4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int a = lane * 4 + k;
-      x[k] = (r < rows && a < ma) ? In[r * ldin + a] : 0.0;
-      mx = fmax(mx, fabs(x[k]));
-    }
+    for (int u = 0; u < OZ_RPW; ++u) {
+      const long r = r0 + u;
+      const double* src = In + r * ldin + a0;
+      if (r < rows && vec && a0 + 3 < ma) {
+        const double2 v0 = __ldg(reinterpret_cast<const double2*>(src));
+        const double2 v1 = __ldg(reinterpret_cast<const double2*>(src) + 1);
+        x[u][0] = v0.x;
+        x[u][1] = v0.y;
+        x[u][2] = v1.x;
+        x[u][3] = v1.y;
+      } else {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    int e = 0;
-    if (mx > 0.0) {
-      frexp(mx, &e);   // mx = f * 2^e, f in [0.5, 1)
-      e += 1;          // |x| * 2^-e <= 0.5
-    }
-    const double sc = pow2(-e);
-    if (lane == 0) ea[r] = pow2(e);
-    const long rt = r >> 7, rl = r & 127;
-    uint32_t* dst = reinterpret_cast<uint32_t*>(A8 + ((rt * ns) * OZ_TM + rl) * OZ_KB) + lane;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) x[k] *= sc;
-    for (int i = 0; i < ns; ++i) {
-      uint32_t pk = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        x[k] *= 128.0;
-        const double q = rint(x[k]);
-        x[k] -= q;
-        pk |= ((uint32_t)(int)q & 0xFFu) << (8 * k);
+        for (int k = 0; k < 4; ++k) x[u][k] = (r < rows && a0 + k < ma) ? __ldg(src + k) : 0.0;
       }
-      dst[(long)i * (OZ_ASLICE / 4)] = pk;
+    }
+#pragma unroll
+    for (int u = 0; u < OZ_RPW; ++u) {
+      const long r = r0 + u;   // < rows_pad: rows_pad is a multiple of 128, hence of OZ_RPW
+      double mx = fmax(fmax(fabs(x[u][0]), fabs(x[u][1])), fmax(fabs(x[u][2]), fabs(x[u][3])));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      int e = 0;
+      if (mx > 0.0) {
+        frexp(mx, &e);   // mx = f * 2^e, f in [0.5, 1)
+        e += 1;          // |x| * 2^-e <= 0.5
+      }
+      const double sc = pow2(-e);
+      if (lane == 0) ea[r] = pow2(e);
+      const long rt = r >> 7, rl = r & 127;
+      uint32_t* dst = reinterpret_cast<uint32_t*>(A8 + ((rt * ns) * OZ_TM + rl) * OZ_KB) + lane;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x[u][k] *= sc;
+      for (int i = 0; i < ns; ++i) {
+        uint32_t pk = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          x[u][k] *= 128.0;
+          const double q = rint(x[u][k]);
+          x[u][k] -= q;
+          pk |= ((uint32_t)(int)q & 0xFFu) << (8 * k);
+        }
+        dst[(long)i * (OZ_ASLICE / 4)] = pk;
+      }
     }
   }
 }
@@ -653,7 +673,7 @@ bool oz_supported(int S, int ma, int ns) { return (S == 2 || S == 4) && ma >= 1 
 
 void oz_slice_rows(cudaStream_t st, const double* In, long ldin, int ma, long rows, int ns, int8_t* A8, double* ea) {
   const long rp = oz_rows_pad(rows);
-  long blocks = (rp + 7) / 8;
+  long blocks = (rp / OZ_RPW + 7) / 8;   // 8 warps per block, OZ_RPW rows per warp and iteration
   if (blocks > 148 * 16) blocks = 148 * 16;
   oz_slice_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(In, ldin, ma, rows, rp, ns, A8, ea);
 }
