@@ -163,6 +163,17 @@ __device__ __forceinline__ void kr_weights_oz(const double* __restrict__ f1, con
   }
 }
 
+// next signed 7-bit digit of x (|x| <= 0.5): q = rint(128 x) as a two's-complement byte, x <- 128 x - q.
+// Round-to-nearest-even through the 1.5 * 2^52 shift (128 x is exact, so the fused add rounds exactly like
+// rint, and the digit sits in the low word of the sum): three FP64 pipe instructions instead of a
+// FRND + F2I pair on the quarter-rate conversion unit, which was what bounded the slicing kernels.
+__device__ __forceinline__ uint32_t oz_digit(double& x) {
+  constexpr double SHIFT = 6755399441055744.0;   // 1.5 * 2^52
+  const double t = fma(x, 128.0, SHIFT);
+  x = fma(x, 128.0, SHIFT - t);                  // SHIFT - t = -q exactly
+  return (uint32_t)__double2loint(t) & 0xFFu;
+}
+
 // ---- slicing ------------------------------------------------------------------------------------
 // one warp per row of In [rows][ldin] (ma <= 128): ea[row] and NS int8 planes, written as
 // A8[rowtile][slice][128 rows][128 bytes]; rows beyond `rows` and columns beyond ma are zero.
@@ -216,12 +227,7 @@ __global__ void __launch_bounds__(256) oz_slice_rows_kernel(const double* __rest
       for (int i = 0; i < ns; ++i) {
         uint32_t pk = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          x[u][k] *= 128.0;
-          const double q = rint(x[u][k]);
-          x[u][k] -= q;
-          pk |= ((uint32_t)(int)q & 0xFFu) << (8 * k);
-        }
+        for (int k = 0; k < 4; ++k) pk |= (uint32_t)oz_digit(x[u][k]) << (8 * k);
         dst[(long)i * (OZ_ASLICE / 4)] = pk;
       }
     }
@@ -263,12 +269,7 @@ __global__ void __launch_bounds__(256) oz_slice_cols_kernel(const double* __rest
   for (int i = 0; i < ns; ++i) {
     uint32_t pk = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      x[k] *= 128.0;
-      const double q = rint(x[k]);
-      x[k] -= q;
-      pk |= ((uint32_t)(int)q & 0xFFu) << (8 * k);
-    }
+    for (int k = 0; k < 4; ++k) pk |= (uint32_t)oz_digit(x[k]) << (8 * k);
     dst[(long)i * (OZ_BSLICE / 4)] = pk;
   }
 }
