@@ -797,6 +797,14 @@ __device__ __forceinline__ void stats_finalize(const double* __restrict__ sp, in
 // all loads in flight at once and stays in registers for the backward contraction (one HBM
 // read per image; the loop version below issued 11 loads per round trip and re-read F).
 // MCH = 0: generic loop version for m > 128.
+// the label-carrying environment is read once per launch (9.6 KB per image, 576 MB per launch at config 3):
+// streaming (evict-first) loads keep it from flushing the operands the neighbouring launches re-read
+// (int8 planes of the thin environment, Q, Z) out of the 126 MB L2
+#ifndef FAT_NO_STREAM
+#define FAT_LDF(p) __ldcs(p)
+#else
+#define FAT_LDF(p) (*(p))
+#endif
 template <int MODE, int MCH>
 __global__ void __launch_bounds__((MCH > 0) ? 384 : 512, 1)
 fat_kernel_t(const double* __restrict__ Q, const double* __restrict__ F, int m,
@@ -831,7 +839,7 @@ fat_kernel_t(const double* __restrict__ Q, const double* __restrict__ F, int m,
         const bool ok = f < m;
         qv[c] = (ok && !(GIVEN_P && DO_Z)) ? q[f] : 0.0;            // FAT_BWD needs no Q
 #pragma unroll
-        for (int l = 0; l < NL; ++l) fv[l][c] = (ok && !(GIVEN_P && DO_ZOUTER)) ? Fn[(long)l * m + f] : 0.0;
+        for (int l = 0; l < NL; ++l) fv[l][c] = (ok && !(GIVEN_P && DO_ZOUTER)) ? FAT_LDF(Fn + (long)l * m + f) : 0.0;
       }
       if (!GIVEN_P) {
 #pragma unroll
