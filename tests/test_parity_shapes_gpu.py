@@ -175,6 +175,12 @@ def test_bond_update_call_one_step_m120(capi, walk120):
     assert abs(r.cg_cost[0] - costs_o[0]) < 1e-10 * costs_o[0]
     assert r.newm == m
     assert abs(r.cost - C2) < 1e-5 * C2
+    # the environment the update advanced -- tcgen05 kernel on the int8 planes that were cut for the
+    # projection of this bond (re-used, not re-cut) -- against the oracle's advance through the SAME new site
+    Wd = list(W)
+    Wd[b] = wk.h.get_site(b)
+    wk.so.shiftE(Wd, b, "Fromleft")
+    assert rel(wk.h.get_env(b), wk.so.slot(b)) < 1e-12
     # restore the walk state: W(b), W(b+1) and the env slot the update advanced
     wk.h.set_site(b, W[b])
     wk.h.set_site(b + 1, W[b + 1])

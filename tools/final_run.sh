@@ -16,6 +16,7 @@ TNML_QR_DEBUG=1 timeout 120 python tools/svd_bench.py > gpurun_out/svd_bench_${T
 timeout 120 tools/umma_bench > gpurun_out/umma_bench_${TAG}.txt 2>&1
 timeout 200 tools/oz_test > gpurun_out/oz_test_${TAG}.txt 2>&1
 bash tools/profile_run.sh ${TAG} > gpurun_out/profile_run.log 2>&1
+bash tools/sanitize_run.sh ${TAG}
 cat gpurun_out/final_pytest.log
 head -c 600 gpurun_out/bench_final.json; echo
 tail -2 gpurun_out/profile_run.log

@@ -155,6 +155,24 @@ int main(int argc, char** argv) {
       float ms, ms_sr, ms_sc, ms_d;
       cudaEventElapsedTime(&ms, e0, e1);
       ms /= reps;
+      // OZ_TEST_FLUSH=1: the same launch with a cold L2 (512 MB memset before every launch), as inside a bond
+      // update where the label-environment stream runs between two projections
+      float ms_cold = 0.f;
+      if (getenv("OZ_TEST_FLUSH")) {
+        static char* flush = nullptr;
+        if (!flush) CK(cudaMalloc(&flush, (size_t)512 << 20));
+        for (int i = 0; i < 10; ++i) {
+          cudaMemsetAsync(flush, i, (size_t)512 << 20);
+          cudaEventRecord(e0);
+          oz_krgemm(0, sh.S, ns, A8, ea, sh.rows, f1, f2, sh.div, B8, eb, sh.J, out, sh.J, 148);
+          cudaEventRecord(e1);
+          CK(cudaDeviceSynchronize());
+          float t;
+          cudaEventElapsedTime(&t, e0, e1);
+          ms_cold += t / 10;
+        }
+        printf("   cold-L2 oz launch: %.4f ms (warm %.4f)\n", ms_cold, ms);
+      }
       cudaEventRecord(e0);
       for (int i = 0; i < reps; ++i) oz_slice_rows(0, in, sh.ma, sh.ma, sh.rows, ns, A8, ea);
       cudaEventRecord(e1);
