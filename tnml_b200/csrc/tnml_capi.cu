@@ -748,7 +748,10 @@ int advance_env(tnml_handle h, int c, int right) {
     variant = e ? atoi(e) : 3;
   }
   bool done = false;
-  if (variant == 3 && hasPrev && NT >= 1024 && kin >= 48 && oz_supported(2, kin, h->oz_slices)) {
+  // (a thin environment whose planes would have to be cut first only from m = 96 on: below that the FP64
+  // kernel, whose cost falls with m^2 where the int8 kernel's K stays padded to 128, is as fast)
+  if (variant == 3 && hasPrev && NT >= 1024 && kin >= 48 && oz_supported(2, kin, h->oz_slices) &&
+      (pe.fat || kin >= 96 || oz_planes_valid(h, pe.p, h->oz_slices))) {
     const int nsl = h->oz_slices;
     TRY(oz_buffers(h, rows, 2, J));
     int nl = 2;
@@ -998,6 +1001,17 @@ int tnml_init_envs(tnml_handle h) {
   for (auto& s : h->slot) {
     s.kind = 0;
     s.host_valid = false;
+  }
+  // size the int8 plane buffers once, for their largest user (the advance of a label-carrying environment,
+  // NL NT rows; class-C operand columns), so that the sweeps never stop for a 0.6 GB allocation
+  {
+    int variant = h->krgemm_variant;
+    if (variant < 0) {
+      const char* e = getenv("TNML_KRGEMM");
+      variant = e ? atoi(e) : 3;
+    }
+    if (variant == 3 && h->NT >= 1024 && h->reserve_m >= 48 && h->reserve_m <= 128)
+      TRY(oz_buffers(h, h->NT * NL, 4, NL * h->reserve_m));
   }
   h->moving = 2;   // building right environments N..3: the high slots are needed last
   for (int n = h->N; n >= 3; --n) TRY(advance_env(h, n, 1));
