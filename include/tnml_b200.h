@@ -183,10 +183,15 @@ int tnml_comm_broadcast(tnml_handle h, double* vals, int n, int root);
  * lives in pinned host memory.  Slots are evicted farthest-next-use first and the slot the next
  * bond needs is fetched on a copy stream while the current bond computes.  Results are bit-identical
  * to the all-resident run.
+ * "krgemm_variant" (per handle; -1 = automatic): kernel of the projection / environment advance.
+ * 3 = tcgen05 int8 error-free splitting (default where it applies: >= 1024 images, 48 <= link
+ * dimension <= 128), 2 = persistent FP64 mma.sync kernel, 1 = register-staged FP64 kernel.
+ * "oz_slices" (per handle, 6..8, default 8): 7-bit planes per operand of variant 3 (8: element
+ * error 1e-15, 7: 1e-13, 6: 1e-11 relative to row scale x column scale).
  * Process-wide variant switches for tests and A/B timing (-1 restores the default):
- * "krgemm_variant" (1: register-staged projection kernel only), "svd_cluster" (0: multi-launch Jacobi
- * instead of the cluster-resident kernel), "svd_cross" (0: full inner tournaments), "svd_precond"
- * (0: plain Jacobi, 1: one QR, 3: column sort + two QRs). */
+ * "krgram_variant", "fat_variant", "svd_cluster" (0: multi-launch Jacobi instead of the
+ * cluster-resident kernel), "svd_cross" (0: full inner tournaments), "svd_precond"
+ * (0: plain Jacobi, 1: one QR, 3: column sort + two QRs).  DESIGN.md section 11 lists them all. */
 int tnml_set_option(tnml_handle h, const char* name, double value);
 
 /* Counters for the roofline report: kernel launches issued by this library,
