@@ -252,6 +252,39 @@ def test_ozaki_slicing_is_error_free_up_to_the_truncation():
     assert errs[0] > 100 * errs[1] and errs[1] > 100 * errs[2]    # about 2^-14 per two slices
 
 
+def test_oz_kernel_model_digits_and_accuracy():
+    """oracle/ozaki.py::oz_kernel_model, the bit-level model of the tcgen05 kernel that was built: round-to-nearest
+    digits through the 1.5 * 2^52 shift equal rint digits bit for bit (ties included), |digit| <= 64, the planes
+    reconstruct the operand to 2^-57 of the row scale, and the modelled product agrees with the float64 contraction
+    to a few 1e-16 of sum |a||b| at 8 planes, 1e-13 at 7, 1e-11 at 6 (the numbers tools/oz_test measures on the GPU)."""
+    from oracle import ozaki
+    rng = np.random.default_rng(2)
+    A = rng.standard_normal((96, 120)) * np.exp(4 * rng.standard_normal((96, 1)))
+    A[5] = 0.0                                                # an all-zero row: scale 1, digits 0
+    A[7, :8] = A[7].max() * np.array([0.5, -0.5, 0.25, 1.0 / 256, -1.0 / 256, 3.0 / 256, 0.5 + 2.0 ** -8, 2.0 ** -20])   # ties
+    qa, sa = ozaki.slices_rn(A, 1, 8, shift_trick=True)
+    qb, sb = ozaki.slices_rn(A, 1, 8, shift_trick=False)
+    assert all(np.array_equal(x, y) for x, y in zip(qa, qb)) and np.array_equal(sa, sb)
+    assert max(int(np.abs(x).max()) for x in qa) <= 64
+    rec = sum(x * 2.0 ** (-7 * (i + 1)) for i, x in enumerate(qa)) * sa
+    assert np.max(np.abs(rec - A) / sa) <= 2.0 ** -57
+    Bm = rng.standard_normal((240, 24)) * np.exp(2 * rng.standard_normal((1, 24)))
+    f1 = np.stack([np.ones(96), rng.random(96) * 1e-2], axis=1)
+    f1[3, 1] = 0.0
+    ref = np.einsum("ra,apj,rp->rj", A, Bm.reshape(120, 2, 24), f1)
+    bound = np.einsum("ra,apj,rp->rj", np.abs(A), np.abs(Bm.reshape(120, 2, 24)), np.abs(f1)) + 1e-300
+    errs = [float(np.max(np.abs(ozaki.oz_kernel_model(A, Bm, f1, None, 2, ns) - ref) / bound)) for ns in (8, 7, 6)]
+    assert errs[0] < 1e-15 and errs[1] < 1e-12 and errs[2] < 1e-10 and errs[1] > 10 * errs[0]
+    # S = 4 (the projection: two feature pairs), one image per 3 rows
+    f2 = np.stack([np.ones(32), rng.random(32)], axis=1)
+    B4 = rng.standard_normal((480, 8))
+    w4 = np.stack([f1[:32, 0] * f2[:, 0], f1[:32, 0] * f2[:, 1], f1[:32, 1] * f2[:, 0], f1[:32, 1] * f2[:, 1]], axis=1)
+    ref4 = np.einsum("ra,apj,rp->rj", A, B4.reshape(120, 4, 8), np.repeat(w4, 3, axis=0))
+    got4 = ozaki.oz_kernel_model(A, B4, f1[:32], f2, 4, 8, div=3)
+    b4 = np.einsum("ra,apj,rp->rj", np.abs(A), np.abs(B4.reshape(120, 4, 8)), np.abs(np.repeat(w4, 3, axis=0))) + 1e-300
+    assert float(np.max(np.abs(got4 - ref4) / b4)) < 1e-15
+
+
 def test_sharded_oracle_equals_whole():
     """tests/helpers.ShardedOracle (the checker of the large-shape GPU tests) == the plain oracle."""
     from tests.helpers import ShardedOracle, make_problem, rel

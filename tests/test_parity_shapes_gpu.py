@@ -312,3 +312,43 @@ def test_tcgen05_projection_matches_dmma_and_oracle(capi, walk120):
     assert rel(res[(3, 6)], res[(2, 8)]) > 0.0          # the 6-plane result is a different computation
     h.set_option("krgemm_variant", -1)
     h.set_option("oz_slices", 8)
+
+
+def test_tcgen05_env_advance_bit_exact(capi):
+    """The tcgen05 int8 path against its operation-by-operation numpy model (oracle/ozaki.py::oz_kernel_model:
+    round-to-nearest 7-bit planes, exact integer level sums, exact merge, two roundings): BIT-IDENTICAL output
+    on (a) the advance of a label-carrying environment (10 NT rows, one image per 10 rows, S = 2) and (b) the
+    advance of a thin environment, both with link dimension 120 (K padded to 128, ragged column tiles).
+    The model itself agrees with the plain float64 contraction to 4e-16 of sum |a||b| (tests/test_oracle.py)."""
+    from oracle import ozaki
+    N, NT = 20, 1024
+    feat, labels, W = make_problem(N=N, NT=NT, m0=120, seed=9)
+    h = capi.Handle(0)
+    h.set_images(feat, labels.astype(np.int32))
+    h.set_mps(W)
+    h.init_envs()
+    # (a) right environments are built N..3 by init_envs: slot 10 (label site) -> slot 9 through site 9
+    prev, new = h.get_env(10), h.get_env(9)
+    assert prev.shape == (NT, 10, 120) and new.shape == (NT, 10, 120)
+    sel = 40
+    Bm = np.ascontiguousarray(W[9].transpose(2, 1, 0)).reshape(2 * W[9].shape[2], W[9].shape[0])   # [(k, s)][j]
+    ref = ozaki.oz_kernel_model(prev[:sel].reshape(sel * 10, 120), Bm, feat[:sel, 8, :], None, 2, 8, div=10)
+    got = new[:sel].reshape(sel * 10, 120)
+    assert np.array_equal(got, ref), float(np.abs(got - ref).max() / np.abs(ref).max())
+    # the same numbers against plain float64: the int8 route is not the less accurate one
+    plain = np.einsum("nlk,jsk,ns->nlj", prev[:sel], W[9], feat[:sel, 8, :]).reshape(sel * 10, 120)
+    assert rel(got, plain) < 1e-14
+    # (b) thin left environment: walk to bond 9, slot 8 -> slot 9
+    for b in range(1, 9):
+        h.set_bond(b)
+        h.shift_env(b, capi.FROMLEFT)
+    prev = h.get_env(8)
+    h.set_bond(9)
+    h.shift_env(9, capi.FROMLEFT)
+    new = h.get_env(9)
+    assert prev.shape == (NT, 120) and new.shape == (NT, 120)
+    sel = 300
+    Bm = W[9].reshape(W[9].shape[0] * 2, W[9].shape[2])                                           # [(k, s)][j]
+    ref = ozaki.oz_kernel_model(prev[:sel], Bm, feat[:sel, 8, :], None, 2, 8)
+    assert np.array_equal(new[:sel], ref), float(np.abs(new[:sel] - ref).max() / np.abs(ref).max())
+    h.close()
