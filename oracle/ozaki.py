@@ -109,3 +109,27 @@ def oz_kernel_model(In: np.ndarray, Bm: np.ndarray, f1: np.ndarray, f2, S: int, 
                 o = float(wf[p] * Fraction(float(v[r, p, j])) + Fraction(o))   # fma: exact, then one rounding to nearest even
             out[r, j] = o
     return out
+
+
+def fat_forward_model(Q: np.ndarray, F: np.ndarray) -> np.ndarray:
+    """P[n][l] = sum_f Q[n][f] F[n][l][f] exactly as `fat_kernel_t<mode, MCH>` (tnml_kernels.cu, m <= 128) rounds it:
+    lane i of the image's warp chains fma over f = i, i + 32, i + 64, i + 96 (starting from 0), then the 32 partial
+    sums are combined by the xor butterfly 16, 8, 4, 2, 1 (plain float64 adds; every lane ends with the same bits)."""
+    from fractions import Fraction
+    n_img, m = Q.shape
+    NL = F.shape[1]
+    assert m <= 128 and F.shape == (n_img, NL, m)
+    part = np.zeros((n_img, NL, 32))
+    for n in range(n_img):
+        qf = [Fraction(float(x)) for x in Q[n]]
+        for l in range(NL):
+            row = F[n, l]
+            for lane in range(32):
+                o = 0.0
+                for f in range(lane, m, 32):
+                    o = float(qf[f] * Fraction(float(row[f])) + Fraction(o))
+                part[n, l, lane] = o
+    idx = np.arange(32)
+    for o in (16, 8, 4, 2, 1):
+        part = part + part[:, :, idx ^ o]
+    return part[:, :, 0]

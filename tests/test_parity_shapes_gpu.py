@@ -352,3 +352,34 @@ def test_tcgen05_env_advance_bit_exact(capi):
     ref = ozaki.oz_kernel_model(prev[:sel], Bm, feat[:sel, 8, :], None, 2, 8)
     assert np.array_equal(new[:sel], ref), float(np.abs(new[:sel] - ref).max() / np.abs(ref).max())
     h.close()
+
+
+def test_tcgen05_projection_and_label_kernel_bit_exact(capi):
+    """Forward pass of a class-L bond at link dimension 120, P = B * t.v (fixedL.cc:318): the projection on the
+    tcgen05 kernel (S = 4: both feature pairs as output-side weights) followed by the label-environment kernel,
+    against the bit-level models of the two kernels (oracle/ozaki.py): BIT-IDENTICAL P on the first 40 images."""
+    from oracle import ozaki
+    N, NT, b = 20, 1024, 8
+    feat, labels, W = make_problem(N=N, NT=NT, m0=120, seed=9)
+    h = capi.Handle(0)
+    h.set_images(feat, labels.astype(np.int32))
+    h.set_mps(W)
+    h.init_envs()
+    for k in range(1, b):
+        h.set_bond(k)
+        h.shift_env(k, capi.FROMLEFT)
+    h.set_bond(b)
+    B = O.form_bond(W[b], W[b + 1])                      # [alpha][s][t][beta] = the device's class-L layout
+    h.bond_load(B)
+    h.quadcost(False)
+    _, P = h.predict(want_P=True)
+    thin, fat = h.get_env(b - 1), h.get_env(b + 2)
+    assert thin.shape == (NT, 120) and fat.shape == (NT, 10, 120)
+    sel = 40
+    Q = ozaki.oz_kernel_model(thin[:sel], B.reshape(120 * 4, 120), feat[:sel, b - 1, :], feat[:sel, b, :], 4, 8)
+    Pm = ozaki.fat_forward_model(Q, fat[:sel])
+    assert np.array_equal(P[:sel], Pm), float(np.abs(P[:sel] - Pm).max() / np.abs(Pm).max())
+    # and the modelled numbers are the float64 contraction to rounding
+    plain = np.einsum("na,astb,ns,nt,nlb->nl", thin[:sel], B, feat[:sel, b - 1, :], feat[:sel, b, :], fat[:sel])
+    assert rel(Pm, plain) < 1e-13
+    h.close()
