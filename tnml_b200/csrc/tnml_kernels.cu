@@ -190,7 +190,7 @@ __device__ __forceinline__ void cp_async8(double* dst, const double* src, int by
 }
 __device__ __forceinline__ void cp_async16(double* dst, const double* src, int bytes) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -837,7 +837,7 @@ fat_kernel_t(const double* __restrict__ Q, const double* __restrict__ F, int m,
       for (int c = 0; c < C; ++c) {
         const int f = lane + 32 * c;
         const bool ok = f < m;
-        qv[c] = (ok && !(GIVEN_P && DO_Z)) ? q[f] : 0.0;            // FAT_BWD needs no Q
+        qv[c] = (ok && !(GIVEN_P && DO_Z)) ? FAT_LDF(q + f) : 0.0;     // FAT_BWD needs no Q; Q is consumed here once
 #pragma unroll
         for (int l = 0; l < NL; ++l) fv[l][c] = (ok && !(GIVEN_P && DO_ZOUTER)) ? FAT_LDF(Fn + (long)l * m + f) : 0.0;
       }
