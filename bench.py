@@ -267,6 +267,16 @@ def cpu_baseline(args, steps=1):
 
 
 def cpu_baseline_structured(args):
+    """All host cores for the BLAS calls even when a launcher pinned OMP_NUM_THREADS=1 (torchrun does)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=os.cpu_count()):
+            return _cpu_baseline_structured(args)
+    except ImportError:
+        return _cpu_baseline_structured(args)
+
+
+def _cpu_baseline_structured(args):
     """BASELINE.md variant (ii): the best-case CPU formulation -- the same Khatri-Rao-structured
     contractions the GPU path uses, as BLAS GEMMs (numpy/OpenBLAS, all host cores) in the oracle -- one
     whole bond update (cgrad + svd + quadcost + shiftE) on a sample of the images, scaled linearly in NT
