@@ -285,6 +285,28 @@ def test_oz_kernel_model_digits_and_accuracy():
     assert float(np.max(np.abs(got4 - ref4) / b4)) < 1e-15
 
 
+def test_golden_one_step_fixture_is_current():
+    """tests/golden/config1_one_step.npz (golden OUTPUT vectors: cost, per-label cost, #correct, first CG pass,
+    truncated bond tensor at 12 bonds of config 1's inputs) is what tests/golden/make_golden_steps.py produces
+    from today's oracle -- a regression pin of the oracle; the GPU path is held to the same file."""
+    import importlib.util
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden_steps", os.path.join(here, "make_golden_steps.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    now = mod.compute()
+    f = np.load(os.path.join(here, "config1_one_step.npz"))
+    assert sorted(f.files) == sorted(now.keys())
+    for k in f.files:
+        a, b = np.asarray(f[k], np.float64), np.asarray(now[k], np.float64)
+        assert a.shape == b.shape, k
+        tol = 1e-7 if k.startswith("rn1_") else 1e-11
+        assert np.abs(a - b).max() <= tol * max(np.abs(a).max(), 1e-300), k
+    # the model function does not depend on the bond it is evaluated at
+    C = [float(f[f"C{b}"][0]) for b in f["bonds"]]
+    assert max(C) - min(C) < 1e-9 * C[0]
+
+
 def test_sharded_oracle_equals_whole():
     """tests/helpers.ShardedOracle (the checker of the large-shape GPU tests) == the plain oracle."""
     from tests.helpers import ShardedOracle, make_problem, rel

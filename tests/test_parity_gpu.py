@@ -205,6 +205,47 @@ def test_golden_mnist_first_bonds(capi):
     h.close()
 
 
+def test_golden_one_step_fixture(capi):
+    """Committed golden OUTPUT vectors (tests/golden/config1_one_step.npz, written by make_golden_steps.py from the
+    oracle on the golden MNIST subset): cost, per-label cost, #correct, cost and |r| after the first CG pass, link
+    dimension and rebuilt bond tensor of the truncated SVD at 12 bonds (edge bonds, class L, both class-C bonds,
+    class R) of the rightward walk with W unchanged.  No oracle code runs here: the CUDA path meets the file."""
+    import os
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    g = np.load(os.path.join(here, "mnist_100_per_label_14x14.npz"))
+    f = np.load(os.path.join(here, "config1_one_step.npz"))
+    feat = O.features(g["sum4"].astype(np.float64) / (4 * 255.0))
+    labels = g["labels"]
+    from tnml_b200 import data as D
+    W = D.random_mps(196, 2, 10, seed=1)
+    chk = sum(float(np.sum(w * w)) for w in W if w is not None)
+    assert abs(chk - float(f["w_checksum"][0])) < 1e-12 * chk           # same seeded MPS as the generator used
+    bonds = set(int(b) for b in f["bonds"])
+    h = _gpu_state(capi, feat, labels, W)
+    for b in range(1, 196):
+        h.set_bond(b)
+        if b in bonds:
+            h.bond_form()
+            c, cl, nc = h.quadcost(False)
+            C = float(f[f"C{b}"][0])
+            assert abs(c - C) < 1e-11 * C, b
+            assert rel(cl, f[f"CL{b}"]) < 1e-10, b
+            assert abs(int(nc) - int(f[f"ncor{b}"][0])) <= 2, b
+            costs, rn = h.cgrad(2)
+            c1, r1 = float(f[f"cost1_{b}"][0]), float(f[f"rn1_{b}"][0])
+            assert abs(costs[0] - c1) < 1e-9 * c1, b
+            assert abs(rn[0] - r1) < 1e-5 * r1, (b, rn[0], r1)
+            h.bond_form()                                               # B = W(b) W(b+1) again
+            gm, _ = h.svd_split(capi.FROMLEFT, 1e-10, 20, 10)
+            assert gm == int(f[f"m{b}"][0]), b
+            assert rel(O.form_bond(h.get_site(b), h.get_site(b + 1)), f[f"newB{b}"]) < 1e-10, b
+            h.set_site(b, W[b])                                         # back to the walk's gauge
+            h.set_site(b + 1, W[b + 1])
+            h.set_bond(b)
+        h.shift_env(b, capi.FROMLEFT)
+    h.close()
+
+
 def test_shards_sum_to_whole(capi):
     """Size-independent property used for multi-GPU: per-shard costs and
     gradients are plain sums over images (fixedL.cc:385,402,421)."""
